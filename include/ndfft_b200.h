@@ -1,0 +1,117 @@
+/*
+ * ndfft_b200.h — C ABI of the B200-native replacement for ndrustfft's hot path:
+ * the batched 1-D transform along one axis of an n-dimensional array.
+ *
+ * The reference (preiter93/ndrustfft v0.5.0, /root/reference/src/lib.rs) has no FFI of its own; its
+ * seam is the public Rust API.  Each entry point below is what a Rust shim (`rust/ndrustfft-b200`)
+ * binds with `extern "C"` to replace one piece of that API:
+ *
+ *   ndfb_plan_create(NDFB_C2C, ..)  <- FftHandler::new        src/lib.rs:294-304 (FftPlanner::plan_fft_forward/inverse)
+ *   ndfb_plan_create(NDFB_R2C, ..)  <- R2cFftHandler::new     src/lib.rs:477-488 (RealFftPlanner)
+ *   ndfb_plan_create(NDFB_DCT, ..)  <- DctHandler::new        src/lib.rs:665-679 (DctPlanner::plan_dct1..4)
+ *   ndfb_plan_destroy               <- Drop of the Arc<dyn ..> plans held by the handlers (src/lib.rs:270-275, 452-458, 641-648)
+ *   ndfb_exec                       <- the bodies of create_transform! / create_transform_par!  src/lib.rs:100-238
+ *                                      together with the per-lane methods they call:
+ *        NDFB_OP_FFT   fft_lane       :313-318     NDFB_OP_IFFT  ifft_lane      :321-331
+ *        NDFB_OP_R2C   fft_r2c_lane   :497-503     NDFB_OP_C2R   ifft_r2c_lane  :506-523
+ *        NDFB_OP_DCT1..4  dct1..4_lane :688-734
+ *   norm = NDFB_NORM_NONE / NDFB_NORM_DEFAULT   <- Normalization::None / ::Default   :89-98, 333-338, 525-531, 736-741
+ *        (Normalization::Custom(fn) is a host function pointer; the shim applies it on the host)
+ *   NDFB_E_SIZE_MISMATCH + ndfb_last_error()    <- assert_size panics  :340-347, 533-540, 743-750
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the boundary; every function
+ * returns 0 or a negative NDFB_E_* code and leaves a thread-local message in ndfb_last_error().
+ * A plan is immutable after creation and may be shared between threads and streams (the handlers
+ * are `Clone` + shared by `&` across rayon workers in the reference, src/lib.rs:169-238).
+ * There is no CPU fallback: without a usable CUDA device every exec returns NDFB_E_CUDA.
+ */
+#ifndef NDFFT_B200_H
+#define NDFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NDFB_API __attribute__((visibility("default")))
+#else
+#define NDFB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ndfb_plan ndfb_plan;
+
+enum ndfb_kind  { NDFB_C2C = 0, NDFB_R2C = 1, NDFB_DCT = 2 };
+enum ndfb_dtype { NDFB_F32 = 0, NDFB_F64 = 1 };
+enum ndfb_op {
+    NDFB_OP_FFT = 0,   /* ndfft      : complex n -> complex n, forward, never scaled                 */
+    NDFB_OP_IFFT = 1,  /* ndifft     : complex n -> complex n, backward, Default = 1/n after          */
+    NDFB_OP_R2C = 2,   /* ndfft_r2c  : real n -> complex n/2+1, never scaled                          */
+    NDFB_OP_C2R = 3,   /* ndifft_r2c : complex n/2+1 -> real n, Default = 1/n, Im(DC), Im(Nyq) ignored */
+    NDFB_OP_DCT1 = 4,  /* nddct1..4  : real n -> real n, Default = scipy (2x rustdct), None = rustdct  */
+    NDFB_OP_DCT2 = 5,
+    NDFB_OP_DCT3 = 6,
+    NDFB_OP_DCT4 = 7
+};
+enum ndfb_norm { NDFB_NORM_NONE = 0, NDFB_NORM_DEFAULT = 1 };
+enum ndfb_mem  { NDFB_MEM_HOST = 0, NDFB_MEM_DEVICE = 1 };
+
+enum ndfb_status {
+    NDFB_OK = 0,
+    NDFB_E_INVALID = -1,        /* bad enum / null pointer / ndim out of range                              */
+    NDFB_E_SIZE_MISMATCH = -2,  /* lane length != handler length ("Size mismatch in fft|dct, got G expected E") */
+    NDFB_E_SHAPE = -3,          /* non-transformed dimensions of input and output differ (ndarray Zip panic)    */
+    NDFB_E_AXIS = -4,           /* axis >= ndim (index panic at src/lib.rs:116)                                 */
+    NDFB_E_ALLOC = -5,
+    NDFB_E_CUDA = -6,           /* CUDA error or no device: the product path never falls back to the CPU        */
+    NDFB_E_UNSUPPORTED = -7     /* length outside what this build plans                         */
+};
+
+#define NDFB_MAX_DIMS 8
+
+/* Build a plan for transforms of logical length n (the handler's `n`: the REAL length for R2C and DCT).
+ * Works without a GPU (tables are uploaded lazily at first exec on `device`). */
+NDFB_API int ndfb_plan_create(ndfb_plan** out, int kind, int dtype, size_t n, int device);
+NDFB_API void ndfb_plan_destroy(ndfb_plan* plan);
+
+/* Writes a JSON description of the schedule each op of this plan would run (kernel family, radix passes,
+ * Bluestein length, tile geometry for a contiguous lane) into buf; returns the length needed. */
+NDFB_API size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap);
+
+/* One nd* call.  shape/strides describe `in` and `out` as ndarray does: `ndim` extents and SIGNED strides
+ * in ELEMENTS of the respective element type (real scalar, or interleaved {re,im} complex).  `mem` says
+ * whether both pointers are host memory (copied through pinned staging; synchronous) or device memory on
+ * the plan's device (asynchronous on `stream`, a cudaStream_t; NULL = default stream). */
+NDFB_API int ndfb_exec(const ndfb_plan* plan, int op, int norm,
+              const void* in, void* out, int ndim,
+              const size_t* shape_in, const ptrdiff_t* strides_in,
+              const size_t* shape_out, const ptrdiff_t* strides_out,
+              int axis, int mem, void* stream);
+
+/* Same, with an explicit extra real factor multiplied into the result (1.0 = none).  Lets the shim fold
+ * simple custom normalisations into the kernel epilogue instead of a host pass. */
+NDFB_API int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale,
+                     const void* in, void* out, int ndim,
+                     const size_t* shape_in, const ptrdiff_t* strides_in,
+                     const size_t* shape_out, const ptrdiff_t* strides_out,
+                     int axis, int mem, void* stream);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+NDFB_API const char* ndfb_last_error(void);
+
+/* Library identification: "ndfft_b200 <version> sm_100a" for the CUDA build. */
+NDFB_API const char* ndfb_version(void);
+
+/* Number of kernel launches issued by this library since load (all threads); used by bench.py to report
+ * `gpu_launches`. */
+NDFB_API uint64_t ndfb_launch_count(void);
+
+/* Release cached workspaces / pinned staging buffers held by the calling thread's pools. */
+NDFB_API void ndfb_release_workspaces(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDFFT_B200_H */

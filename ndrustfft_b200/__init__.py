@@ -1,0 +1,281 @@
+"""ndrustfft_b200 — B200-native drop-in for ndrustfft's axis-transform hot path.
+
+Host-side mirror of the reference's public API (preiter93/ndrustfft v0.5.0, src/lib.rs):
+
+    Normalization {None, Default, Custom(fn)}          src/lib.rs:89-98
+    FftHandler / R2cFftHandler / DctHandler            src/lib.rs:270-311, 452-495, 641-686
+    ndfft, ndifft, ndfft_r2c, ndifft_r2c, nddct1..4    src/lib.rs:350-397, 543-587, 753-834
+    *_par twins                                        src/lib.rs:399-421, 589-611, 777-844
+
+Same names, argument order `(input, output, handler, axis)` and error behaviour (size-mismatch text, axis range,
+shape agreement).  Arrays are numpy arrays (host path: staged through the GPU) or torch CUDA tensors / anything with
+`data_ptr()`, `shape`, `stride()` (device path: zero-copy, asynchronous on the current torch stream).  All
+arithmetic runs in hand-written sm_100a kernels behind the C ABI of include/ndfft_b200.h; there is no CPU path.
+On the GPU every call is already parallel over all lanes, so the `_par` functions are the same entry points.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import NdfftError, SizeMismatch  # noqa: F401
+
+__all__ = [
+    "Normalization", "FftHandler", "R2cFftHandler", "DctHandler",
+    "ndfft", "ndifft", "ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4",
+    "ndfft_par", "ndifft_par", "ndfft_r2c_par", "ndifft_r2c_par",
+    "nddct1_par", "nddct2_par", "nddct3_par", "nddct4_par",
+    "NdfftError", "SizeMismatch", "Backend",
+]
+
+
+class Normalization:
+    """`Normalization<T>` (src/lib.rs:89-98): `Normalization.None_`, `.Default`, `.Custom(fn)`.
+
+    `fn(lane)` receives one 1-D numpy lane and mutates it in place, exactly where the reference calls it:
+    after the inverse C2C transform (src/lib.rs:329), on the spectrum copy before C2R (src/lib.rs:514), on the
+    input copy before a DCT (src/lib.rs:695).  It is a host function, so `Custom` stages lanes through the host;
+    `None_` and `Default` are fused into the kernels."""
+
+    def __init__(self, kind, func=None):
+        self.kind = kind
+        self.func = func
+
+    @classmethod
+    def Custom(cls, func):
+        return cls("custom", func)
+
+    def __repr__(self):
+        return f"Normalization.{self.kind}"
+
+
+Normalization.None_ = Normalization("none")
+Normalization.Default = Normalization("default")
+
+
+def _real_dtype(dtype):
+    dt = np.dtype(dtype)
+    if dt == np.float32 or dt == np.complex64:
+        return np.dtype(np.float32)
+    if dt == np.float64 or dt == np.complex128:
+        return np.dtype(np.float64)
+    raise TypeError(f"unsupported dtype {dt}; ndrustfft supports f32 and f64 (FftNum, src/lib.rs:111)")
+
+
+class _Handler:
+    _kind = None
+
+    def __init__(self, n, dtype=np.float64, device=0, backend=None):
+        self.n = int(n)
+        self.dtype = _real_dtype(dtype)
+        self.device = int(device)
+        self.norm = Normalization.Default
+        self._backend = backend or _default_backend()
+        self._plan = ctypes.c_void_p()
+        lib = self._backend.lib
+        lib.check(lib.dll.ndfb_plan_create(ctypes.byref(self._plan), self._kind,
+                                          _lib.F32 if self.dtype == np.float32 else _lib.F64, self.n, self.device))
+
+    def normalization(self, norm):
+        """Builder, like the reference's `fn normalization(mut self, norm) -> Self`."""
+        self.norm = norm
+        return self
+
+    def describe(self):
+        import json
+        lib = self._backend.lib
+        need = lib.dll.ndfb_plan_describe(self._plan, None, 0)
+        buf = ctypes.create_string_buffer(int(need))
+        lib.dll.ndfb_plan_describe(self._plan, buf, need)
+        return json.loads(buf.value.decode())
+
+    def __del__(self):
+        try:
+            if self._plan:
+                self._backend.lib.dll.ndfb_plan_destroy(self._plan)
+                self._plan = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class FftHandler(_Handler):
+    """`FftHandler<T>::new(n)` (src/lib.rs:294-304)."""
+    _kind = _lib.C2C
+
+
+class R2cFftHandler(_Handler):
+    """`R2cFftHandler<T>::new(n)` (src/lib.rs:477-488); `m = n/2 + 1`."""
+    _kind = _lib.R2C
+
+    def __init__(self, n, dtype=np.float64, device=0, backend=None):
+        super().__init__(n, dtype, device, backend)
+        self.m = self.n // 2 + 1
+
+
+class DctHandler(_Handler):
+    """`DctHandler<T>::new(n)` (src/lib.rs:665-679)."""
+    _kind = _lib.DCT
+
+
+# ------------------------------------------------------------------------------------------------------
+# array adapters
+# ------------------------------------------------------------------------------------------------------
+class _View:
+    __slots__ = ("ptr", "shape", "strides", "dtype", "device", "obj", "stream")
+
+
+def _view_of(arr):
+    v = _View()
+    v.obj = arr
+    v.stream = None
+    if isinstance(arr, np.ndarray):
+        item = arr.dtype.itemsize
+        for s in arr.strides:
+            if s % item:
+                raise ValueError("array strides must be multiples of the element size")
+        v.ptr = arr.ctypes.data
+        v.shape = tuple(arr.shape)
+        v.strides = tuple(s // item for s in arr.strides)
+        v.dtype = arr.dtype
+        v.device = None
+        return v
+    if hasattr(arr, "data_ptr") and hasattr(arr, "stride"):  # torch tensor
+        import torch
+        v.ptr = arr.data_ptr()
+        v.shape = tuple(arr.shape)
+        v.strides = tuple(arr.stride())
+        v.dtype = np.dtype({torch.float32: np.float32, torch.float64: np.float64,
+                            torch.complex64: np.complex64, torch.complex128: np.complex128}[arr.dtype])
+        if arr.is_cuda:
+            v.device = arr.device.index if arr.device.index is not None else torch.cuda.current_device()
+            v.stream = torch.cuda.current_stream(arr.device).cuda_stream
+        else:
+            v.device = None
+        return v
+    raise TypeError(f"unsupported array type {type(arr)}")
+
+
+class Backend:
+    """The nd* functions bound to one loaded C library."""
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def _exec(self, handler, op, inp, out, axis, norm_code, extra_scale=1.0):
+        vi, vo = _view_of(inp), _view_of(out)
+        if len(vi.shape) != len(vo.shape):
+            raise AssertionError("input and output must have the same number of dimensions")
+        ndim = len(vi.shape)
+        if ndim < 1:
+            raise IndexError("0-dimensional arrays have no axis")
+        want_in_cx = op in (_lib.OP_FFT, _lib.OP_IFFT, _lib.OP_C2R)
+        want_out_cx = op in (_lib.OP_FFT, _lib.OP_IFFT, _lib.OP_R2C)
+        rd = handler.dtype
+        cd = np.dtype(np.complex64 if rd == np.float32 else np.complex128)
+        if vi.dtype != (cd if want_in_cx else rd) or vo.dtype != (cd if want_out_cx else rd):
+            raise TypeError(f"element types do not match the handler: got {vi.dtype} -> {vo.dtype}, "
+                            f"expected {(cd if want_in_cx else rd)} -> {(cd if want_out_cx else rd)}")
+        if (vi.device is None) != (vo.device is None):
+            raise ValueError("input and output must both be host arrays or both be device tensors")
+        if vi.device is not None and (vi.device != handler.device or vo.device != handler.device):
+            raise ValueError("tensors must live on the handler's device")
+        if not (0 <= int(axis) < ndim):
+            raise IndexError(f"axis {axis} out of range for {ndim}-dimensional array")
+        SZ = ctypes.c_size_t * ndim
+        PD = ctypes.c_ssize_t * ndim
+        mem = _lib.MEM_HOST if vi.device is None else _lib.MEM_DEVICE
+        rc = self.lib.dll.ndfb_exec_scaled(
+            handler._plan, op, norm_code, float(extra_scale), ctypes.c_void_p(vi.ptr), ctypes.c_void_p(vo.ptr), ndim,
+            SZ(*vi.shape), PD(*vi.strides), SZ(*vo.shape), PD(*vo.strides), int(axis), mem,
+            ctypes.c_void_p(vi.stream or 0))
+        self.lib.check(rc)
+
+    # -- Custom normalisation plumbing (host callback) --
+    @staticmethod
+    def _to_host(a):
+        return a if isinstance(a, np.ndarray) else a.detach().cpu().numpy()
+
+    @staticmethod
+    def _assign(dst, src_np):
+        if isinstance(dst, np.ndarray):
+            dst[...] = src_np
+        else:
+            import torch
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src_np)))
+
+    @staticmethod
+    def _apply_lanes(func, arr, axis):
+        moved = np.moveaxis(arr, axis, -1)
+        tmp = np.ascontiguousarray(moved)
+        for lane in tmp.reshape(-1, tmp.shape[-1]):
+            func(lane)
+        moved[...] = tmp
+
+    def _run(self, handler, op, inp, out, axis):
+        norm = handler.norm
+        if norm.kind == "none":
+            return self._exec(handler, op, inp, out, axis, _lib.NORM_NONE)
+        if norm.kind == "default":
+            return self._exec(handler, op, inp, out, axis, _lib.NORM_DEFAULT)
+        # Custom(fn)
+        if op in (_lib.OP_FFT, _lib.OP_R2C):          # forward transforms never normalise (src/lib.rs:313-318, 497-503)
+            return self._exec(handler, op, inp, out, axis, _lib.NORM_NONE)
+        if op == _lib.OP_IFFT:                        # after the transform, on the output lane (src/lib.rs:329)
+            self._exec(handler, op, inp, out, axis, _lib.NORM_NONE)
+            host = np.array(self._to_host(out))
+            self._apply_lanes(norm.func, host, axis)
+            return self._assign(out, host)
+        # C2R / DCT: on a copy of the input lane, before the transform (src/lib.rs:514, 695)
+        host = np.array(self._to_host(inp))
+        self._apply_lanes(norm.func, host, axis)
+        if isinstance(inp, np.ndarray):
+            staged = host
+        else:
+            import torch
+            staged = torch.from_numpy(host).to(inp.device)
+        return self._exec(handler, op, staged, out, axis, _lib.NORM_NONE)
+
+    def ndfft(self, input, output, handler, axis): self._run(handler, _lib.OP_FFT, input, output, axis)
+    def ndifft(self, input, output, handler, axis): self._run(handler, _lib.OP_IFFT, input, output, axis)
+    def ndfft_r2c(self, input, output, handler, axis): self._run(handler, _lib.OP_R2C, input, output, axis)
+    def ndifft_r2c(self, input, output, handler, axis): self._run(handler, _lib.OP_C2R, input, output, axis)
+    def nddct1(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT1, input, output, axis)
+    def nddct2(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT2, input, output, axis)
+    def nddct3(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT3, input, output, axis)
+    def nddct4(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT4, input, output, axis)
+    ndfft_par, ndifft_par = ndfft, ndifft
+    ndfft_r2c_par, ndifft_r2c_par = ndfft_r2c, ndifft_r2c
+    nddct1_par, nddct2_par, nddct3_par, nddct4_par = nddct1, nddct2, nddct3, nddct4
+
+    # handler constructors bound to this backend
+    def FftHandler(self, n, dtype=np.float64, device=0): return FftHandler(n, dtype, device, backend=self)
+    def R2cFftHandler(self, n, dtype=np.float64, device=0): return R2cFftHandler(n, dtype, device, backend=self)
+    def DctHandler(self, n, dtype=np.float64, device=0): return DctHandler(n, dtype, device, backend=self)
+
+
+_backend = None
+
+
+def _default_backend():
+    global _backend
+    if _backend is None:
+        _backend = Backend(_lib.default_lib())   # raises ImportError if the CUDA library is not built
+    return _backend
+
+
+def ndfft(input, output, handler, axis): handler._backend.ndfft(input, output, handler, axis)
+def ndifft(input, output, handler, axis): handler._backend.ndifft(input, output, handler, axis)
+def ndfft_r2c(input, output, handler, axis): handler._backend.ndfft_r2c(input, output, handler, axis)
+def ndifft_r2c(input, output, handler, axis): handler._backend.ndifft_r2c(input, output, handler, axis)
+def nddct1(input, output, handler, axis): handler._backend.nddct1(input, output, handler, axis)
+def nddct2(input, output, handler, axis): handler._backend.nddct2(input, output, handler, axis)
+def nddct3(input, output, handler, axis): handler._backend.nddct3(input, output, handler, axis)
+def nddct4(input, output, handler, axis): handler._backend.nddct4(input, output, handler, axis)
+
+
+# `_par` twins (feature "parallel", Cargo.toml:39): on the GPU the serial entry points already run every lane in parallel.
+ndfft_par, ndifft_par = ndfft, ndifft
+ndfft_r2c_par, ndifft_r2c_par = ndfft_r2c, ndifft_r2c
+nddct1_par, nddct2_par, nddct3_par, nddct4_par = nddct1, nddct2, nddct3, nddct4

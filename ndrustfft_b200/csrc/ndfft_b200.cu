@@ -1,0 +1,685 @@
+// ndfft_b200.cu — C ABI (include/ndfft_b200.h), launch geometry and device plumbing.
+//
+// Built two ways from the same sources:
+//   nvcc -gencode arch=compute_100a,code=sm_100a  -> ndrustfft_b200/lib/libndfft_b200.so   (THE product)
+//   g++ -x c++ -DNDFB_EMU                         -> tests/emu/libndfft_b200_emu.so        (test-only SIMT emulation,
+//                                                    never loaded by the package; see tests/emu/simt_emu.h)
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ndfft_b200.h"
+#include "common.h"
+#include "plan.h"
+#include "tile_kernel.cuh"
+
+namespace ndfb {
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+static std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------------
+// device plumbing (CUDA, or plain host memory in the emulation build)
+// ------------------------------------------------------------------------------------------------------
+#ifdef NDFB_EMU
+typedef void* stream_t;
+static int dev_set(int) { return 0; }
+static int dev_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : NDFB_E_ALLOC; }
+static void dev_free(void* p) { std::free(p); }
+static int dev_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memcpy(d, h, bytes); return 0; }
+static int dev_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); return 0; }
+static int dev_sync(stream_t) { return 0; }
+static size_t dev_smem_cap(int) { return 227 * 1024; }
+static int dev_sm_count(int) { return 148; }
+template <typename K>
+static int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stream_t, const TileArgs& a) {
+    TileArgs copy = a;
+    simt::launch(dim3(grid), dim3(block), smem, [&]() { kernel(copy); });
+    g_launches++;
+    return 0;
+}
+static const char* kVersion = "ndfft_b200 0.1 emu (CPU SIMT emulation, tests only)";
+#else
+typedef cudaStream_t stream_t;
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(NDFB_E_CUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+#define NDFB_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
+    } while (0)
+static int dev_set(int dev) { NDFB_CUDA(cudaSetDevice(dev)); return 0; }
+static int dev_malloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(NDFB_E_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    return 0;
+}
+static void dev_free(void* p) { cudaFree(p); }
+static int dev_h2d(void* d, const void* h, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); return 0; }
+static int dev_d2h(void* h, const void* d, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); return 0; }
+static int dev_sync(stream_t s) { NDFB_CUDA(cudaStreamSynchronize(s)); return 0; }
+static size_t dev_smem_cap(int dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 227 * 1024; }
+    return (size_t)v;
+}
+static int dev_sm_count(int dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 148; }
+    return v;
+}
+template <typename K>
+static int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stream_t s, const TileArgs& a) {
+    static thread_local std::map<const void*, size_t> attr_set;
+    const void* key = (const void*)kernel;
+    auto it = attr_set.find(key);
+    if (it == attr_set.end() || it->second < smem) {
+        NDFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        attr_set[key] = 227 * 1024;
+    }
+    kernel<<<grid, block, smem, s>>>(a);
+    NDFB_CUDA(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+static const char* kVersion = "ndfft_b200 0.1 sm_100a";
+#endif
+
+// ------------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------------
+struct DeviceTables {
+    void *tw = nullptr, *tabA = nullptr, *tabB = nullptr, *blu_c = nullptr, *blu_bhat = nullptr;
+    uint32_t* perm = nullptr;
+    void *fs_lo = nullptr, *fs_hi = nullptr;
+    bool ready = false;
+};
+
+struct Core {
+    CoreTables t;
+    DeviceTables d;
+    std::mutex mu;
+};
+
+template <typename R>
+static int upload_cx(void** dst, const std::vector<cld>& v) {
+    if (v.empty()) { *dst = nullptr; return 0; }
+    std::vector<Cx<R>> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) { h[i].x = (R)v[i].real(); h[i].y = (R)v[i].imag(); }
+    int rc = dev_malloc(dst, h.size() * sizeof(Cx<R>));
+    if (rc) return rc;
+    rc = dev_h2d(*dst, h.data(), h.size() * sizeof(Cx<R>), 0);
+    if (rc) return rc;
+    return dev_sync(0);
+}
+
+}  // namespace ndfb
+
+struct ndfb_plan {
+    int kind, dtype, device;
+    size_t n;
+    std::mutex mu;
+    std::map<std::pair<int, int>, std::unique_ptr<ndfb::Core>> cores;  // (tile kind, n) -> schedule
+    // four-step inter-pass twiddles, keyed by total length
+    struct FsTw { void *lo = nullptr, *hi = nullptr; int shift = 0; };
+    std::map<long long, FsTw> fs;
+};
+
+namespace ndfb {
+
+static Core* get_core(ndfb_plan* p, int tk, int n) {
+    std::lock_guard<std::mutex> g(p->mu);
+    auto key = std::make_pair(tk, n);
+    auto it = p->cores.find(key);
+    if (it != p->cores.end()) return it->second.get();
+    std::unique_ptr<Core> c(new Core());
+    build_core(c->t, tk, n);
+    Core* raw = c.get();
+    p->cores[key] = std::move(c);
+    return raw;
+}
+
+template <typename R>
+static int ensure_device(ndfb_plan* p, Core* c) {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (c->d.ready) return 0;
+    int rc = dev_set(p->device);
+    if (rc) return rc;
+    if ((rc = upload_cx<R>(&c->d.tw, c->t.tw))) return rc;
+    if ((rc = upload_cx<R>(&c->d.tabA, c->t.tabA))) return rc;
+    if ((rc = upload_cx<R>(&c->d.tabB, c->t.tabB))) return rc;
+    if ((rc = upload_cx<R>(&c->d.blu_c, c->t.blu_c))) return rc;
+    if ((rc = upload_cx<R>(&c->d.blu_bhat, c->t.blu_bhat))) return rc;
+    if (!c->t.perm.empty()) {
+        void* q = nullptr;
+        if ((rc = dev_malloc(&q, c->t.perm.size() * 4))) return rc;
+        if ((rc = dev_h2d(q, c->t.perm.data(), c->t.perm.size() * 4, 0))) return rc;
+        if ((rc = dev_sync(0))) return rc;
+        c->d.perm = (uint32_t*)q;
+    }
+    c->d.ready = true;
+    return 0;
+}
+
+template <typename R>
+static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->fs.find(Ntot);
+    if (it != p->fs.end()) { *out = it->second; return 0; }
+    int shift = 0;
+    while ((1LL << (2 * shift)) < Ntot) ++shift;  // lo table ~ sqrt(N)
+    if (shift < 1) shift = 1;
+    const long long nlo = 1LL << shift, nhi = ((Ntot - 1) >> shift) + 1;
+    std::vector<cld> lo(nlo), hi(nhi);
+    for (long long a = 0; a < nlo; ++a) lo[a] = unit_root(a, Ntot);
+    for (long long b = 0; b < nhi; ++b) hi[b] = unit_root(b << shift, Ntot);
+    ndfb_plan::FsTw t;
+    t.shift = shift;
+    int rc;
+    if ((rc = dev_set(p->device))) return rc;
+    if ((rc = upload_cx<R>(&t.lo, lo))) return rc;
+    if ((rc = upload_cx<R>(&t.hi, hi))) return rc;
+    p->fs[Ntot] = t;
+    *out = t;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// workspaces (per host thread)
+// ------------------------------------------------------------------------------------------------------
+struct Pool {
+    struct Slot { void* p = nullptr; size_t bytes = 0; int device = -1; };
+    Slot slots[3];
+    ~Pool() {}  // device memory is reclaimed at process exit; explicit release via ndfb_release_workspaces
+    int get(int which, int device, size_t bytes, void** out) {
+        Slot& s = slots[which];
+        if (s.p && (s.bytes < bytes || s.device != device)) { dev_free(s.p); s.p = nullptr; s.bytes = 0; }
+        if (!s.p) {
+            int rc = dev_malloc(&s.p, bytes);
+            if (rc) { s.p = nullptr; return rc; }
+            s.bytes = bytes;
+            s.device = device;
+        }
+        *out = s.p;
+        return 0;
+    }
+    void release() {
+        for (auto& s : slots) { if (s.p) dev_free(s.p); s.p = nullptr; s.bytes = 0; }
+    }
+};
+static thread_local Pool g_pool;
+
+// ------------------------------------------------------------------------------------------------------
+// launch geometry
+// ------------------------------------------------------------------------------------------------------
+struct BDim { long long size, is, os; };
+
+static long long llabs_(long long v) { return v < 0 ? -v : v; }
+static int pow2floor(long long v) { int p = 1; while ((long long)p * 2 <= v) p *= 2; return p; }
+static int pow2ceil(long long v) { int p = 1; while (p < v) p *= 2; return p; }
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+struct LaunchSpec {
+    // one tile-kernel launch over `dims` batch dims
+    Core* core;
+    const void* in;
+    void* out;
+    std::vector<BDim> dims;  // batch dims, fastest first (already ordered/merged)
+    long long is_axis, os_axis;
+    int conj_in = 0, conj_out = 0;
+    double scale = 1.0;
+    int fs_twiddle = 0;
+    ndfb_plan::FsTw fs;
+    bool keep_dim_order = false;
+};
+
+template <typename R>
+static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::string* describe = nullptr) {
+    Core* c = s.core;
+    const CoreTables& t = c->t;
+    TileArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.in = s.in; a.out = s.out;
+    a.kind = t.kind; a.n = t.n; a.n_in = t.n_in; a.n_out = t.n_out; a.N = t.N; a.M = t.M;
+    a.is_axis = s.is_axis; a.os_axis = s.os_axis;
+    a.conj_in = s.conj_in; a.conj_out = s.conj_out;
+    a.scale = s.scale;
+    a.npass = (int)t.radix.size();
+    if (a.npass > kMaxPass) return fail(NDFB_E_UNSUPPORTED, "too many radix passes (%d)", a.npass);
+    for (int i = 0; i < a.npass; ++i) a.radix[i] = t.radix[i];
+    a.pad_shift = 31;
+
+    long long nlanes = 1;
+    for (auto& d : s.dims) nlanes *= d.size;
+    if (nlanes == 0 || t.n_out == 0) return 0;
+    a.nlanes = nlanes;
+    if ((int)s.dims.size() > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "internal: too many batch dims");
+    a.nbd = (int)s.dims.size();
+    for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
+
+    const size_t in_elem = (t.in_complex ? 2 : 1) * sizeof(R), out_elem = (t.out_complex ? 2 : 1) * sizeof(R);
+    const size_t cs = sizeof(Cx<R>);
+    const bool have_batch = a.nbd > 0 && nlanes > 1;
+    a.in_lane_fast = have_batch && t.n_in > 1 && llabs_(a.bis[0]) < llabs_(s.is_axis);
+    a.out_lane_fast = have_batch && t.n_out > 1 && llabs_(a.bos[0]) < llabs_(s.os_axis);
+    const bool strided = a.in_lane_fast || a.out_lane_fast;
+
+    const size_t cap = dev_smem_cap(p->device) - 1024;
+    const size_t lane_bytes = (size_t)t.Bl * cs;
+    const size_t per_lane_over = 2 * sizeof(long long) + sizeof(int);
+    long long Lmax = (long long)(cap / (lane_bytes + per_lane_over));
+    if (Lmax < 1) return fail(NDFB_E_UNSUPPORTED, "lane of %d complex points does not fit in shared memory", t.Bl);
+    Lmax = pow2floor(Lmax);
+    long long Lwant;
+    if (strided) {
+        size_t minelem = std::min(in_elem, out_elem);
+        Lwant = std::max<long long>(1, 128 / (long long)minelem);
+        // keep the tile modest when the lanes are long, but never below one 32-byte sector per row
+        while (Lwant * lane_bytes > 64 * 1024 && Lwant * minelem > 32) Lwant /= 2;
+    } else {
+        Lwant = pow2floor(std::max<long long>(1, (long long)(32 * 1024 / cs) / t.Bl));
+        const int sms = dev_sm_count(p->device);
+        while (Lwant > 1 && (nlanes + Lwant - 1) / Lwant < 2LL * sms) Lwant /= 2;
+    }
+    long long L = std::min<long long>(std::min(Lwant, Lmax), pow2ceil(nlanes));
+    if (L > 512) L = 512;
+    a.L = (int)L;
+    a.log2L = ilog2(a.L);
+    a.Bl = t.Bl;
+    if (strided && a.L > 1) { a.LP = 1; a.EP = a.L; }
+    else { a.LP = t.Bl; a.EP = 1; }
+    long long work = (long long)a.L * std::max(t.B, 1);
+    int T = pow2ceil((work + 7) / 8);
+    T = std::max(64, std::min(512, T));
+    if (T < a.L) T = std::min(512, a.L);
+
+    a.tw = c->d.tw; a.tabA = c->d.tabA; a.tabB = c->d.tabB; a.perm = c->d.perm;
+    a.blu_c = c->d.blu_c; a.blu_bhat = c->d.blu_bhat;
+    a.fs_twiddle = s.fs_twiddle;
+    a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
+
+    size_t smem = (((size_t)a.L * per_lane_over + 15) & ~(size_t)15) + (size_t)a.L * lane_bytes;
+    const long long grid = (nlanes + a.L - 1) / a.L;
+    if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+    if (describe) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "{\"kernel\":\"tile_kernel<%s,%s>\",\"L\":%d,\"threads\":%d,\"smem\":%zu,\"grid\":%lld,\"layout\":\"%s\"}",
+                 sizeof(R) == 4 ? "f32" : "f64", t.M ? "bluestein" : "direct", a.L, T, smem, grid, a.EP == 1 ? "lane-major" : "interleaved");
+        *describe = buf;
+        return 0;
+    }
+    if (t.M) return dev_launch(tile_kernel<R, true>, (unsigned)grid, (unsigned)T, smem, stream, a);
+    return dev_launch(tile_kernel<R, false>, (unsigned)grid, (unsigned)T, smem, stream, a);
+}
+
+// order batch dims by input stride and merge the ones that are contiguous in both arrays
+static void normalize_dims(std::vector<BDim>& dims) {
+    std::vector<BDim> v;
+    for (auto& d : dims) if (d.size != 1) v.push_back(d);
+    std::stable_sort(v.begin(), v.end(), [](const BDim& x, const BDim& y) {
+        if (llabs_(x.is) != llabs_(y.is)) return llabs_(x.is) < llabs_(y.is);
+        return llabs_(x.os) < llabs_(y.os);
+    });
+    std::vector<BDim> m;
+    for (auto& d : v) {
+        if (!m.empty() && d.is == m.back().is * m.back().size && d.os == m.back().os * m.back().size) m.back().size *= d.size;
+        else m.push_back(d);
+    }
+    dims.swap(m);
+}
+
+static bool fits_one_tile(ndfb_plan* p, const CoreTables& t, size_t cs) {
+    const size_t cap = dev_smem_cap(p->device) - 1024;
+    return (size_t)t.Bl * cs + 64 <= cap;
+}
+
+// C2C of a length too long for one CTA's shared memory: four-step N = N1*N2 through a device workspace.
+template <typename R>
+static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale, const void* in, void* out,
+                          std::vector<BDim> dims, long long is_axis, long long os_axis, stream_t stream) {
+    const size_t cs = sizeof(Cx<R>);
+    const size_t cap = dev_smem_cap(p->device) - 1024;
+    const long long cap1 = (long long)(cap / (4 * cs + 64));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
+    const long long cap2 = (long long)(cap / (cs + 64));
+    if (!is_smooth(N)) return fail(NDFB_E_UNSUPPORTED, "length %lld has a prime factor > 13 and is too long for the single-pass Bluestein kernel", N);
+    // N1 * N2 = N, N1 <= cap1, N2 <= cap2, as square as possible
+    long long best1 = 0;
+    for (long long d = 1; d * d <= N; ++d) {
+        if (N % d) continue;
+        long long cands[2] = {d, N / d};
+        for (long long n1 : cands) {
+            long long n2 = N / n1;
+            if (n1 > cap1 || n2 > cap2 || n1 < 2 || n2 < 2) continue;
+            if (best1 == 0 || llabs_(n1 - n2) < llabs_(best1 - N / best1)) best1 = n1;
+        }
+    }
+    if (!best1) return fail(NDFB_E_UNSUPPORTED, "length %lld is too long for the two-pass decomposition (max about %lld)", N, cap1 * cap2);
+    const long long N1 = best1, N2 = N / N1;
+    normalize_dims(dims);
+    if ((int)dims.size() + 1 > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "four-step transform with more than %d batch dims", kMaxBatchDims - 1);
+    long long nb = 1;
+    for (auto& d : dims) nb *= d.size;
+    void* ws = nullptr;
+    int rc = g_pool.get(2, p->device, (size_t)nb * (size_t)N * cs, &ws);
+    if (rc) return rc;
+    Core* c1 = get_core(p, TK_C2C, (int)N1);
+    Core* c2 = get_core(p, TK_C2C, (int)N2);
+    if ((rc = ensure_device<R>(p, c1))) return rc;
+    if ((rc = ensure_device<R>(p, c2))) return rc;
+    ndfb_plan::FsTw fs;
+    if ((rc = get_fs_twiddles<R>(p, N, &fs))) return rc;
+    // pass 1: lanes (j2, batch...), transform over j1 (stride N2), twiddle W_N^{k1 j2}; ws[b][k1][j2]
+    LaunchSpec s1;
+    s1.core = c1; s1.in = in; s1.out = ws;
+    s1.dims.push_back({N2, is_axis, 1});
+    long long wstride = N;
+    for (auto& d : dims) { s1.dims.push_back({d.size, d.is, wstride}); wstride *= d.size; }
+    s1.is_axis = N2 * is_axis; s1.os_axis = N2;
+    s1.conj_in = inverse; s1.fs_twiddle = 1; s1.fs = fs;
+    if ((rc = launch_tile<R>(p, s1, stream))) return rc;
+    // pass 2: lanes (k1, batch...), transform over j2 (contiguous), out[k1 + N1*k2]
+    LaunchSpec s2;
+    s2.core = c2; s2.in = ws; s2.out = out;
+    s2.dims.push_back({N1, N2, os_axis});
+    wstride = N;
+    for (auto& d : dims) { s2.dims.push_back({d.size, wstride, d.os}); wstride *= d.size; }
+    s2.is_axis = 1; s2.os_axis = N1 * os_axis;
+    s2.conj_out = inverse; s2.scale = scale;
+    return launch_tile<R>(p, s2, stream);
+}
+
+struct OpInfo {
+    int tk;
+    bool in_complex, out_complex;
+    long long n_in, n_out;
+    int conj_in = 0, conj_out = 0;
+    double scale = 1.0;
+    const char* what = "fft";
+};
+
+static int op_info(const ndfb_plan* p, int op, int norm, OpInfo* o) {
+    const long long n = (long long)p->n;
+    const long long m = n / 2 + 1;
+    const bool def = norm == NDFB_NORM_DEFAULT;
+    switch (op) {
+        case NDFB_OP_FFT:
+        case NDFB_OP_IFFT:
+            if (p->kind != NDFB_C2C) return fail(NDFB_E_INVALID, "op %d needs a C2C plan", op);
+            o->tk = TK_C2C; o->in_complex = o->out_complex = true; o->n_in = o->n_out = n;
+            if (op == NDFB_OP_IFFT) { o->conj_in = o->conj_out = 1; o->scale = def && n > 0 ? 1.0 / (double)n : 1.0; }
+            return 0;
+        case NDFB_OP_R2C:
+            if (p->kind != NDFB_R2C) return fail(NDFB_E_INVALID, "op %d needs an R2C plan", op);
+            o->tk = (n % 2 == 0 && n >= 2) ? TK_R2C_EVEN : TK_R2C_ODD;
+            o->in_complex = false; o->out_complex = true; o->n_in = n; o->n_out = m;
+            return 0;
+        case NDFB_OP_C2R:
+            if (p->kind != NDFB_R2C) return fail(NDFB_E_INVALID, "op %d needs an R2C plan", op);
+            o->tk = (n % 2 == 0 && n >= 2) ? TK_C2R_EVEN : TK_C2R_ODD;
+            o->in_complex = true; o->out_complex = false; o->n_in = m; o->n_out = n;
+            o->scale = def && n > 0 ? 1.0 / (double)n : 1.0;
+            return 0;
+        case NDFB_OP_DCT1: case NDFB_OP_DCT2: case NDFB_OP_DCT3: case NDFB_OP_DCT4: {
+            if (p->kind != NDFB_DCT) return fail(NDFB_E_INVALID, "op %d needs a DCT plan", op);
+            const bool even = n % 2 == 0 && n >= 2;
+            if (op == NDFB_OP_DCT1) o->tk = TK_DCT1;
+            else if (op == NDFB_OP_DCT2) o->tk = even ? TK_DCT2_EVEN : TK_DCT2_ODD;
+            else if (op == NDFB_OP_DCT3) o->tk = even ? TK_DCT3_EVEN : TK_DCT3_ODD;
+            else o->tk = even ? TK_DCT4_EVEN : TK_DCT4_ODD;
+            o->in_complex = o->out_complex = false; o->n_in = o->n_out = n;
+            o->scale = def ? 2.0 : 1.0;
+            o->what = "dct";
+            return 0;
+        }
+        default: return fail(NDFB_E_INVALID, "unknown op %d", op);
+    }
+}
+
+template <typename R>
+static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, int ndim,
+                       const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
+                       const ptrdiff_t* strides_out, int axis, stream_t stream) {
+    int rc = dev_set(p->device);
+    if (rc) return rc;
+    std::vector<BDim> dims;
+    for (int d = 0; d < ndim; ++d)
+        if (d != axis) dims.push_back({(long long)shape_in[d], (long long)strides_in[d], (long long)strides_out[d]});
+    for (auto& d : dims) if (d.size == 0) return 0;
+    if (p->n == 0) return 0;
+    const long long is_axis = strides_in[axis], os_axis = strides_out[axis];
+    const double scale = o.scale * extra_scale;
+    const size_t cs = sizeof(Cx<R>);
+
+    if (o.tk == TK_DCT1 && p->n < 2) return fail(NDFB_E_UNSUPPORTED, "DCT-I needs n >= 2");
+    if (p->n > (size_t)(1 << 30)) return fail(NDFB_E_UNSUPPORTED, "length %zu too long", p->n);
+    Core* c = nullptr;
+    bool single = true;
+    {
+        // estimate lane slots before building the (possibly huge) tables
+        long long N_est = (long long)p->n;
+        if (o.tk == TK_R2C_EVEN || o.tk == TK_C2R_EVEN || o.tk == TK_DCT2_EVEN || o.tk == TK_DCT3_EVEN || o.tk == TK_DCT4_EVEN) N_est = p->n / 2;
+        if (o.tk == TK_DCT4_ODD) N_est = 2 * (long long)p->n;
+        const size_t cap = dev_smem_cap(p->device) - 1024;
+        if ((size_t)N_est * cs + 64 > cap) single = false;
+    }
+    if (single) {
+        c = get_core(p, o.tk, (int)p->n);
+        if (!fits_one_tile(p, c->t, cs)) single = false;
+    }
+    if (!single) {
+        if (o.tk != TK_C2C)
+            return fail(NDFB_E_UNSUPPORTED, "%s of length %zu does not fit one CTA's shared memory; only complex-to-complex has a multi-pass path in this build", o.what, p->n);
+        return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, in, out, dims, is_axis, os_axis, stream);
+    }
+    if ((rc = ensure_device<R>(p, c))) return rc;
+    normalize_dims(dims);
+    // more batch dims than the kernel indexes: peel the slowest ones on the host
+    if ((int)dims.size() > kMaxBatchDims) {
+        std::vector<BDim> inner(dims.begin(), dims.begin() + kMaxBatchDims);
+        std::vector<BDim> outer(dims.begin() + kMaxBatchDims, dims.end());
+        long long nouter = 1;
+        for (auto& d : outer) nouter *= d.size;
+        const size_t ie = (o.in_complex ? 2 : 1) * sizeof(R), oe = (o.out_complex ? 2 : 1) * sizeof(R);
+        for (long long g = 0; g < nouter; ++g) {
+            long long rem = g, io = 0, oo = 0;
+            for (auto& d : outer) { long long r = rem % d.size; rem /= d.size; io += r * d.is; oo += r * d.os; }
+            LaunchSpec s;
+            s.core = c; s.in = (const char*)in + io * (long long)ie; s.out = (char*)out + oo * (long long)oe;
+            s.dims = inner; s.is_axis = is_axis; s.os_axis = os_axis;
+            s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
+            if ((rc = launch_tile<R>(p, s, stream))) return rc;
+        }
+        return 0;
+    }
+    LaunchSpec s;
+    s.core = c; s.in = in; s.out = out; s.dims = dims; s.is_axis = is_axis; s.os_axis = os_axis;
+    s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
+    return launch_tile<R>(p, s, stream);
+}
+
+// byte span [lo, hi) touched by a strided array, relative to its base pointer
+static void span_of(int ndim, const size_t* shape, const ptrdiff_t* strides, size_t elem, long long* lo, long long* hi, bool* dense) {
+    long long mn = 0, mx = 0, count = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] == 0) { *lo = 0; *hi = 0; *dense = true; return; }
+        long long ext = (long long)(shape[d] - 1) * (long long)strides[d];
+        if (ext < 0) mn += ext; else mx += ext;
+        count *= (long long)shape[d];
+    }
+    *lo = mn * (long long)elem;
+    *hi = (mx + 1) * (long long)elem;
+    *dense = (mx - mn + 1) == count;
+}
+
+template <typename R>
+static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, int ndim,
+                    const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
+                    const ptrdiff_t* strides_out, int axis, int mem, void* stream_v) {
+    stream_t stream = (stream_t)stream_v;
+    if (mem == NDFB_MEM_DEVICE)
+        return exec_device<R>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, stream);
+    // host arrays: move the touched byte spans through device staging buffers, strides unchanged
+    const size_t ie = (o.in_complex ? 2 : 1) * sizeof(R), oe = (o.out_complex ? 2 : 1) * sizeof(R);
+    long long ilo, ihi, olo, ohi;
+    bool idense, odense;
+    span_of(ndim, shape_in, strides_in, ie, &ilo, &ihi, &idense);
+    span_of(ndim, shape_out, strides_out, oe, &olo, &ohi, &odense);
+    if (ihi == ilo || ohi == olo) return 0;
+    int rc = dev_set(p->device);
+    if (rc) return rc;
+    void *din = nullptr, *dout = nullptr;
+    if ((rc = g_pool.get(0, p->device, (size_t)(ihi - ilo), &din))) return rc;
+    if ((rc = g_pool.get(1, p->device, (size_t)(ohi - olo), &dout))) return rc;
+    if ((rc = dev_h2d(din, (const char*)in + ilo, (size_t)(ihi - ilo), stream))) return rc;
+    if (!odense) {  // keep the bytes between output elements intact
+        if ((rc = dev_h2d(dout, (const char*)out + olo, (size_t)(ohi - olo), stream))) return rc;
+    }
+    rc = exec_device<R>(p, o, extra_scale, (const char*)din - ilo, (char*)dout - olo, ndim, shape_in, strides_in,
+                        shape_out, strides_out, axis, stream);
+    if (rc) return rc;
+    if ((rc = dev_d2h((char*)out + olo, dout, (size_t)(ohi - olo), stream))) return rc;
+    return dev_sync(stream);
+}
+
+}  // namespace ndfb
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+using namespace ndfb;
+
+extern "C" {
+
+int ndfb_plan_create(ndfb_plan** out, int kind, int dtype, size_t n, int device) {
+    if (!out) return fail(NDFB_E_INVALID, "null plan pointer");
+    if (kind < NDFB_C2C || kind > NDFB_DCT) return fail(NDFB_E_INVALID, "unknown plan kind %d", kind);
+    if (dtype != NDFB_F32 && dtype != NDFB_F64) return fail(NDFB_E_INVALID, "unknown dtype %d", dtype);
+    if (device < 0) return fail(NDFB_E_INVALID, "negative device index");
+    ndfb_plan* p = new (std::nothrow) ndfb_plan();
+    if (!p) return fail(NDFB_E_ALLOC, "out of host memory");
+    p->kind = kind; p->dtype = dtype; p->device = device; p->n = n;
+    *out = p;
+    return NDFB_OK;
+}
+
+void ndfb_plan_destroy(ndfb_plan* p) {
+    if (!p) return;
+    for (auto& kv : p->cores) {
+        DeviceTables& d = kv.second->d;
+        void* ptrs[] = {d.tw, d.tabA, d.tabB, d.blu_c, d.blu_bhat, d.perm};
+        for (void* q : ptrs) if (q) dev_free(q);
+    }
+    for (auto& kv : p->fs) { if (kv.second.lo) dev_free(kv.second.lo); if (kv.second.hi) dev_free(kv.second.hi); }
+    delete p;
+}
+
+static int check_call(const ndfb_plan* p, const OpInfo& o, int ndim, const size_t* shape_in, const size_t* shape_out, int axis) {
+    // order of checks mirrors the reference: axis index (src/lib.rs:116), lane sizes (assert_size: input first,
+    // then output; src/lib.rs:314-315, 498-499, 507-508, 689-690), then ndarray's Zip shape check.
+    if (axis < 0 || axis >= ndim) return fail(NDFB_E_AXIS, "axis %d out of range for %d-dimensional array", axis, ndim);
+    if ((long long)shape_in[axis] != o.n_in)
+        return fail(NDFB_E_SIZE_MISMATCH, "Size mismatch in %s, got %zu expected %lld", o.what, shape_in[axis], o.n_in);
+    if ((long long)shape_out[axis] != o.n_out)
+        return fail(NDFB_E_SIZE_MISMATCH, "Size mismatch in %s, got %zu expected %lld", o.what, shape_out[axis], o.n_out);
+    for (int d = 0; d < ndim; ++d)
+        if (d != axis && shape_in[d] != shape_out[d])
+            return fail(NDFB_E_SHAPE, "input and output shapes differ along dimension %d (%zu vs %zu)", d, shape_in[d], shape_out[d]);
+    (void)p;
+    return 0;
+}
+
+int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale, const void* in, void* out, int ndim,
+                     const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
+                     const ptrdiff_t* strides_out, int axis, int mem, void* stream) {
+    if (!plan || !shape_in || !strides_in || !shape_out || !strides_out) return fail(NDFB_E_INVALID, "null argument");
+    if (ndim < 1 || ndim > NDFB_MAX_DIMS) return fail(NDFB_E_INVALID, "ndim %d outside 1..%d", ndim, NDFB_MAX_DIMS);
+    if (norm != NDFB_NORM_NONE && norm != NDFB_NORM_DEFAULT) return fail(NDFB_E_INVALID, "unknown norm %d", norm);
+    if (mem != NDFB_MEM_HOST && mem != NDFB_MEM_DEVICE) return fail(NDFB_E_INVALID, "unknown mem %d", mem);
+    ndfb_plan* p = const_cast<ndfb_plan*>(plan);  // lazily built caches are guarded by mutexes
+    OpInfo o;
+    int rc = op_info(p, op, norm, &o);
+    if (rc) return rc;
+    if ((rc = check_call(p, o, ndim, shape_in, shape_out, axis))) return rc;
+    bool empty = false;
+    for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) empty = true;
+    if (empty) return NDFB_OK;
+    if (!in || !out) return fail(NDFB_E_INVALID, "null data pointer");
+    if (p->dtype == NDFB_F32)
+        return exec_any<float>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+    return exec_any<double>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+}
+
+int ndfb_exec(const ndfb_plan* plan, int op, int norm, const void* in, void* out, int ndim, const size_t* shape_in,
+              const ptrdiff_t* strides_in, const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem,
+              void* stream) {
+    return ndfb_exec_scaled(plan, op, norm, 1.0, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+}
+
+size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {
+    if (!plan) return 0;
+    ndfb_plan* p = const_cast<ndfb_plan*>(plan);
+    std::string s = "{\"kind\":" + std::to_string(p->kind) + ",\"dtype\":\"" + (p->dtype == NDFB_F32 ? "f32" : "f64") +
+                    "\",\"n\":" + std::to_string(p->n) + ",\"ops\":[";
+    int first_op = p->kind == NDFB_C2C ? NDFB_OP_FFT : p->kind == NDFB_R2C ? NDFB_OP_R2C : NDFB_OP_DCT1;
+    int last_op = p->kind == NDFB_C2C ? NDFB_OP_IFFT : p->kind == NDFB_R2C ? NDFB_OP_C2R : NDFB_OP_DCT4;
+    bool first = true;
+    for (int op = first_op; op <= last_op; ++op) {
+        OpInfo o;
+        if (op_info(p, op, NDFB_NORM_DEFAULT, &o)) continue;
+        if (!first) s += ",";
+        first = false;
+        s += "{\"op\":" + std::to_string(op) + ",\"tile_kind\":" + std::to_string(o.tk);
+        const size_t cs = p->dtype == NDFB_F32 ? 8 : 16;
+        long long N_est = (long long)p->n;
+        if (o.tk == TK_R2C_EVEN || o.tk == TK_C2R_EVEN || o.tk == TK_DCT2_EVEN || o.tk == TK_DCT3_EVEN || o.tk == TK_DCT4_EVEN) N_est = p->n / 2;
+        if (o.tk == TK_DCT4_ODD) N_est = 2 * (long long)p->n;
+        if (o.tk == TK_DCT1) N_est = (long long)p->n - 1;
+        if (p->n == 0 || (o.tk == TK_DCT1 && p->n < 2)) { s += ",\"family\":\"empty\"}"; continue; }
+        if ((size_t)N_est * cs + 64 > 226 * 1024) {
+            s += std::string(",\"family\":\"") + (o.tk == TK_C2C && is_smooth((long long)p->n) ? "four-step" : "unsupported") + "\",\"N\":" + std::to_string(N_est) + "}";
+            continue;
+        }
+        Core* c = get_core(p, o.tk, (int)p->n);
+        s += ",\"family\":\"" + std::string(c->t.M ? "bluestein" : "direct") + "\",\"N\":" + std::to_string(c->t.N) +
+             ",\"M\":" + std::to_string(c->t.M) + ",\"radix\":[";
+        for (size_t i = 0; i < c->t.radix.size(); ++i) s += (i ? "," : "") + std::to_string(c->t.radix[i]);
+        s += "],\"lane_slots\":" + std::to_string(c->t.Bl) + "}";
+    }
+    s += "]}";
+    if (buf && cap) {
+        size_t ncopy = std::min(cap - 1, s.size());
+        std::memcpy(buf, s.data(), ncopy);
+        buf[ncopy] = 0;
+    }
+    return s.size() + 1;
+}
+
+const char* ndfb_last_error(void) { return g_err.c_str(); }
+const char* ndfb_version(void) { return kVersion; }
+uint64_t ndfb_launch_count(void) { return g_launches.load(); }
+void ndfb_release_workspaces(void) { g_pool.release(); }
+
+}  // extern "C"
