@@ -485,6 +485,12 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         const size_t cap = dev_smem_cap(p->device) - 1024;
         if ((size_t)N_est * cs + 64 > cap) single = false;
     }
+    // test hook: exercise the two-pass path at sizes the emulator/tests can afford
+    if (single && o.tk == TK_C2C && p->n >= 4 && std::getenv("NDFB_FORCE_FOUR_STEP")) {
+        bool composite = false;
+        for (size_t d = 2; d * d <= p->n; ++d) if (p->n % d == 0) composite = true;
+        if (composite && is_smooth((long long)p->n)) single = false;
+    }
     if (single) {
         c = get_core(p, o.tk, (int)p->n);
         if (!fits_one_tile(p, c->t, cs)) single = false;

@@ -81,6 +81,25 @@ Normalization.Default = Normalization(Normalization.DEFAULT)
 Normalization.Custom = Normalization.custom
 
 
+# Precision of the engine calls.  Default: always f64 (the oracle is the yardstick for the f32 kernels too).
+# bench.py's CPU-baseline legs switch to the handler's own precision so that the timed port does the same
+# arithmetic the reference would (rustfft on Complex<f32>), not an f64 detour.
+_NATIVE = False
+
+
+def set_native_precision(flag):
+    global _NATIVE
+    _NATIVE = bool(flag)
+
+
+def _rdt(h):
+    return np.float32 if (_NATIVE and h.dtype == np.float32) else np.float64
+
+
+def _cdt(h):
+    return np.complex64 if (_NATIVE and h.dtype == np.float32) else np.complex128
+
+
 def _workers(par):
     return (os.cpu_count() or 1) if par else 1
 
@@ -170,14 +189,14 @@ def _c2c(inp, out, h, axis, inverse, par):
     _check_shapes(inp, out, axis)
     _check_lane("fft", inp.shape[axis], h.n)   # src/lib.rs:314 / 322
     _check_lane("fft", out.shape[axis], h.n)   # src/lib.rs:315 / 323
-    x = np.asarray(inp, dtype=np.complex128)
+    x = np.asarray(inp, dtype=_cdt(h))
     if not inverse:
         y = _sfft.fft(x, axis=axis, workers=_workers(par))  # src/lib.rs:316-317
     else:
         # plan_bwd.process is unscaled (src/lib.rs:324-325): numpy's ifft * n
         y = _sfft.ifft(x, axis=axis, norm="forward", workers=_workers(par))
         if h.norm.kind == Normalization.DEFAULT:      # src/lib.rs:328, 333-338
-            y = y * (1.0 / h.n)
+            y *= y.dtype.type(1.0 / h.n).real
         elif h.norm.kind == "custom":                 # src/lib.rs:329 (after the transform)
             y = np.array(y)
             _apply_custom(h.norm.func, y, axis)
@@ -188,7 +207,7 @@ def _r2c(inp, out, h, axis, par):
     _check_shapes(inp, out, axis)
     _check_lane("fft", inp.shape[axis], h.n)   # src/lib.rs:498
     _check_lane("fft", out.shape[axis], h.m)   # src/lib.rs:499
-    x = np.asarray(inp, dtype=np.float64)
+    x = np.asarray(inp, dtype=_rdt(h))
     out[...] = _sfft.rfft(x, axis=axis, workers=_workers(par))  # src/lib.rs:500-502, never scaled
 
 
@@ -196,7 +215,7 @@ def _c2r(inp, out, h, axis, par):
     _check_shapes(inp, out, axis)
     _check_lane("fft", inp.shape[axis], h.m)   # src/lib.rs:507
     _check_lane("fft", out.shape[axis], h.n)   # src/lib.rs:508
-    buf = np.array(inp, dtype=np.complex128)   # src/lib.rs:509-510 (copy)
+    buf = np.array(inp, dtype=_cdt(h))         # src/lib.rs:509-510 (copy)
     if h.norm.kind == Normalization.DEFAULT:   # src/lib.rs:513, 525-531: spectrum * 1/n BEFORE the transform
         buf *= 1.0 / h.n
     elif h.norm.kind == "custom":              # src/lib.rs:514: f sees the m-long spectrum copy
@@ -215,7 +234,7 @@ def _dct(inp, out, h, axis, kind, par):
     _check_shapes(inp, out, axis)
     _check_lane("dct", inp.shape[axis], h.n)   # src/lib.rs:689 ...
     _check_lane("dct", out.shape[axis], h.n)   # src/lib.rs:690 ...
-    buf = np.array(inp, dtype=np.float64)      # src/lib.rs:691 (copy)
+    buf = np.array(inp, dtype=_rdt(h))         # src/lib.rs:691 (copy)
     if h.norm.kind == Normalization.DEFAULT:   # src/lib.rs:694, 736-741: input * 2 BEFORE the transform
         buf *= 2.0
     elif h.norm.kind == "custom":              # src/lib.rs:695

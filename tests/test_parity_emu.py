@@ -1,0 +1,169 @@
+"""Kernel-logic parity on the CPU: the CUDA kernel sources compiled with g++ against tests/emu/simt_emu.h
+(one fiber per CUDA thread) and compared with the oracle.  Small sizes only; the parity tests proper are
+tests/test_parity_gpu.py (-m gpu), which run the same cases through the nvcc-built library on a B200."""
+import numpy as np
+import pytest
+
+from emu_backend import emu_backend
+from parity_cases import Harness, seeded
+from oracle import ndrustfft_oracle as orc
+
+OPS = ["ndfft", "ndifft", "ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4"]
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return Harness(emu_backend())
+
+
+def test_reference_unit_tests(hs):
+    hs.reference_unit_tests()
+
+
+# every radix, their products, Bluestein lengths, n = 1, 2
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 16, 17, 23, 26, 32, 45, 49, 60, 64, 77, 97, 121, 128, 169, 240])
+@pytest.mark.parametrize("op", OPS)
+def test_lengths_contiguous(hs, op, n):
+    if op == "nddct1" and n < 2:
+        pytest.skip("DCT-I needs n >= 2")
+    hs.run(op, n, (3, n), 1, np.float64, seed=n)
+
+
+@pytest.mark.parametrize("n", [2, 6, 12, 17, 30, 64, 100])
+@pytest.mark.parametrize("op", OPS)
+def test_f32(hs, op, n):
+    hs.run(op, n, (4, n), 1, np.float32, seed=100 + n)
+    hs.run(op, n, (n, 5), 0, np.float32, seed=200 + n)
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("shape,axis", [((12, 7), 0), ((5, 12, 3), 1), ((12, 3, 4), 0), ((2, 3, 12), 2), ((2, 3, 2, 12, 2), 3), ((12,), 0)])
+def test_layout_paths(hs, op, shape, axis):
+    n = shape[axis]
+    hs.run(op, n, shape, axis, np.float64, seed=7)          # path A / B
+    hs.run(op, n, shape, axis, np.float64, seed=8, order="F")  # path C
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_norm_none(hs, op):
+    hs.run(op, 10, (3, 10), 1, np.float64, norm="none", seed=3)
+    hs.run(op, 9, (9, 4), 0, np.float64, norm="none", seed=4)
+
+
+@pytest.mark.parametrize("op", ["ndfft", "nddct2", "ndfft_r2c"])
+def test_par_aliases(hs, op):
+    hs.run(op, 12, (5, 12), 1, par=True)
+
+
+def test_many_lanes_tail_tiles(hs):
+    # lane counts that are not multiples of the tile width, both layouts
+    hs.run("ndfft", 16, (37, 16), 1, seed=1)
+    hs.run("ndfft", 16, (16, 37), 0, seed=2)
+    hs.run("nddct2", 20, (20, 3, 11), 0, seed=3)
+
+
+def test_strided_views_and_negative_strides(hs):
+    be = hs.be
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, (8, 20)) + 1j * rng.uniform(-1, 1, (8, 20))
+    x = base[::2, ::-2]                       # shape (4, 10), negative stride along the axis
+    assert x.strides[1] < 0
+    out_base = np.full((4, 25), 7 + 7j)
+    y = out_base[:, 3:23:2]                    # non-dense output view: holes must be preserved
+    h = be.FftHandler(10)
+    be.ndfft(x, y, h, 1)
+    yo = np.zeros((4, 10), complex)
+    orc.ndfft(np.ascontiguousarray(x), yo, orc.FftHandler(10), 1)
+    assert orc.rel_l2(y, yo) < 1e-12
+    mask = np.ones(25, bool); mask[3:23:2] = False
+    assert np.all(out_base[:, mask] == 7 + 7j)
+
+
+def test_custom_normalization_all_kinds(hs):
+    be = hs.be
+    Norm = type(be.FftHandler(4).norm)
+    rng = np.random.default_rng(11)
+
+    def f(lane):
+        lane *= 0.25
+        lane[0] += 1.0
+
+    n = 8
+    # c2c inverse: after the transform (src/lib.rs:329)
+    x = rng.uniform(-1, 1, (3, n)) + 1j * rng.uniform(-1, 1, (3, n))
+    y = np.zeros_like(x); yo = np.zeros_like(x)
+    be.ndifft(x, y, be.FftHandler(n).normalization(Norm.Custom(f)), 1)
+    orc.ndifft(x, yo, orc.FftHandler(n).normalization(orc.Normalization.custom(f)), 1)
+    assert orc.rel_l2(y, yo) < 1e-12
+    # c2r: on the m-long spectrum copy, before; Im(DC)/Im(Nyq) zeroed afterwards (src/lib.rs:511-521)
+    sp = rng.uniform(-1, 1, (3, n // 2 + 1)) + 1j * rng.uniform(-1, 1, (3, n // 2 + 1))
+    r = np.zeros((3, n)); ro = np.zeros((3, n))
+    be.ndifft_r2c(sp, r, be.R2cFftHandler(n).normalization(Norm.Custom(f)), 1)
+    orc.ndifft_r2c(sp, ro, orc.R2cFftHandler(n).normalization(orc.Normalization.custom(f)), 1)
+    assert orc.rel_l2(r, ro) < 1e-12
+    # dct: on the input copy, before (src/lib.rs:692-696)
+    xr = rng.uniform(-1, 1, (n, 3))
+    for k in (1, 2, 3, 4):
+        r = np.zeros((n, 3)); ro = np.zeros((n, 3))
+        getattr(be, f"nddct{k}")(xr, r, be.DctHandler(n).normalization(Norm.Custom(f)), 0)
+        getattr(orc, f"nddct{k}")(xr, ro, orc.DctHandler(n).normalization(orc.Normalization.custom(f)), 0)
+        assert orc.rel_l2(r, ro) < 1e-12
+
+
+def test_roundtrip_identities(hs):
+    be = hs.be
+    n = 24
+    x = seeded(1, (5, n), np.float64, False)
+    a = np.zeros_like(x); b = np.zeros_like(x)
+    h = be.DctHandler(n)
+    be.nddct2(x, a, h, 1); be.nddct3(a, b, h, 1)
+    assert orc.rel_l2(b, 2 * n * x) < 1e-12
+    be.nddct1(x, a, h, 1); be.nddct1(a, b, h, 1)
+    assert orc.rel_l2(b, 2 * (n - 1) * x) < 1e-12
+    be.nddct4(x, a, h, 1); be.nddct4(a, b, h, 1)
+    assert orc.rel_l2(b, 2 * n * x) < 1e-12
+    xc = seeded(2, (n, 3), np.float64, True)
+    ya = np.zeros_like(xc); yb = np.zeros_like(xc)
+    hf = be.FftHandler(n)
+    be.ndfft(xc, ya, hf, 0); be.ndifft(ya, yb, hf, 0)
+    assert orc.rel_l2(yb, xc) < 1e-12
+
+
+def test_errors(hs):
+    be = hs.be
+    h = be.FftHandler(6)
+    with pytest.raises(AssertionError, match="Size mismatch in fft, got 5 expected 6"):
+        be.ndfft(np.zeros((2, 5), complex), np.zeros((2, 5), complex), h, 1)
+    with pytest.raises(AssertionError, match="Size mismatch in fft, got 7 expected 6"):
+        be.ndfft(np.zeros((2, 6), complex), np.zeros((2, 7), complex), h, 1)
+    with pytest.raises(AssertionError, match="Size mismatch in dct, got 5 expected 6"):
+        be.nddct3(np.zeros((5, 2)), np.zeros((5, 2)), be.DctHandler(6), 0)
+    hr = be.R2cFftHandler(6)
+    with pytest.raises(AssertionError, match="Size mismatch in fft, got 6 expected 4"):
+        be.ndfft_r2c(np.zeros((2, 6)), np.zeros((2, 6), complex), hr, 1)
+    with pytest.raises(AssertionError):   # ndarray Zip shape mismatch
+        be.ndfft(np.zeros((2, 6), complex), np.zeros((3, 6), complex), h, 1)
+    with pytest.raises(IndexError):
+        be.ndfft(np.zeros((2, 6), complex), np.zeros((2, 6), complex), h, 2)
+    with pytest.raises(TypeError):
+        be.ndfft(np.zeros((2, 6)), np.zeros((2, 6), complex), h, 1)
+
+
+def test_empty_arrays(hs):
+    be = hs.be
+    be.ndfft(np.zeros((0, 6), complex), np.zeros((0, 6), complex), be.FftHandler(6), 1)
+    be.ndfft(np.zeros((3, 0), complex), np.zeros((3, 0), complex), be.FftHandler(0), 1)
+
+
+def test_four_step_decomposition_small(hs):
+    """The two-pass path (exec_four_step) is normally taken only for rows that overflow shared memory; the
+    NDFB_FORCE_FOUR_STEP hook lets the emulator exercise it at a size it can finish."""
+    import os
+    os.environ["NDFB_FORCE_FOUR_STEP"] = "1"
+    try:
+        hs.run("ndfft", 64, (3, 64), 1, seed=5)
+        hs.run("ndifft", 60, (2, 60), 1, seed=6)
+        hs.run("ndfft", 48, (48, 3), 0, seed=7)
+        hs.run("ndifft", 36, (2, 36, 2), 1, np.float32, seed=8)
+    finally:
+        del os.environ["NDFB_FORCE_FOUR_STEP"]

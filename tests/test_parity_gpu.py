@@ -1,0 +1,356 @@
+"""The parity tests proper: the nvcc-built sm_100a library, called through the C ABI, against the oracle.
+
+Small/medium cases compare whole arrays; at BASELINE.json's full sizes (c2..c5) a seeded subset of lanes is
+compared with the oracle (lanes are independent, src/lib.rs:120-124) and size-independent identities
+(round trips, DCT scale factors, linearity) cover the whole array.
+Tolerances: relative L2 <= 1e-12 (f64), <= 1e-5 (f32)  (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from parity_cases import Harness, TOL, cdt  # noqa: E402
+from oracle import ndrustfft_oracle as orc  # noqa: E402
+
+OPS = ["ndfft", "ndifft", "ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4"]
+TDT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+       np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}
+
+
+def _backend():
+    import ndrustfft_b200 as nb
+    be = nb._default_backend()
+    assert "sm_100a" in be.lib.version()
+    return be
+
+
+class DevHarness(Harness):
+    def __init__(self, be):
+        super().__init__(be,
+                         mk=lambda a: torch.from_numpy(np.array(a)).cuda(),
+                         to_np=lambda t: t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t),
+                         zeros=lambda shape, dt: torch.zeros(tuple(shape), dtype=TDT[np.dtype(dt)], device="cuda"))
+
+    def mk_f(self, a):
+        t = torch.from_numpy(np.asfortranarray(np.array(a))).cuda()
+        assert t.stride(0) == 1
+        return t
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return DevHarness(_backend())
+
+
+@pytest.fixture(scope="module")
+def host():
+    return Harness(_backend())  # numpy arrays -> NDFB_MEM_HOST staging path
+
+
+def test_native_library_is_the_one_running(dev):
+    be = dev.be
+    before = be.lib.launch_count()
+    dev.run("ndfft", 64, (8, 64), 1)
+    assert be.lib.launch_count() == before + 1
+    assert be.lib.path.endswith("ndrustfft_b200/lib/libndfft_b200.so")
+
+
+def test_reference_unit_tests_device(dev):
+    dev.reference_unit_tests()
+
+
+def test_reference_unit_tests_host(host):
+    host.reference_unit_tests()
+
+
+LENGTHS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 16, 17, 25, 27, 32, 49, 64, 81, 97, 100, 121, 125, 128, 129, 169,
+           243, 256, 264, 343, 360, 384, 500, 512, 513, 625, 1000, 1009, 1024, 1025, 2048, 2187, 4095, 4096]
+
+
+@pytest.mark.parametrize("n", LENGTHS)
+def test_lengths_f64(dev, n):
+    for op in OPS:
+        if op == "nddct1" and n < 2:
+            continue
+        dev.run(op, n, (5, n), 1, np.float64, seed=n)
+        dev.run(op, n, (n, 6), 0, np.float64, seed=n + 1)
+
+
+@pytest.mark.parametrize("n", [2, 6, 16, 17, 30, 64, 100, 128, 243, 360, 1000, 1009, 1024, 4096, 8192])
+def test_lengths_f32(dev, n):
+    for op in OPS:
+        dev.run(op, n, (7, n), 1, np.float32, seed=n)
+        dev.run(op, n, (n, 9), 0, np.float32, seed=n + 1)
+
+
+@pytest.mark.parametrize("n", [4099, 5003])
+def test_long_bluestein(dev, n):
+    dev.run("ndfft", n, (3, n), 1, np.float32, seed=n)
+    dev.run("ndifft", n, (n, 3), 0, np.float32, seed=n)
+    if n <= 4099:
+        dev.run("ndfft", n, (3, n), 1, np.float64, seed=n)
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("shape,axis", [((40, 33), 0), ((17, 40, 9), 1), ((40, 5, 6), 0), ((4, 5, 40), 2),
+                                        ((2, 3, 2, 40, 2), 3), ((40,), 0), ((3, 2, 2, 2, 2, 40), 5), ((3, 2, 40, 2, 2, 2), 2)])
+def test_layout_paths(dev, host, op, shape, axis):
+    n = shape[axis]
+    dev.run(op, n, shape, axis, np.float64, seed=7)
+    dev.run(op, n, shape, axis, np.float64, seed=8, order="F")
+    host.run(op, n, shape, axis, np.float32, seed=9)
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_norm_none(dev, op):
+    dev.run(op, 100, (30, 100), 1, np.float64, norm="none", seed=3)
+    dev.run(op, 99, (99, 40), 0, np.float64, norm="none", seed=4)
+
+
+def test_strided_views_host(host):
+    be = host.be
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, (8, 20)) + 1j * rng.uniform(-1, 1, (8, 20))
+    x = base[::2, ::-2]
+    out_base = np.full((4, 25), 7 + 7j)
+    y = out_base[:, 3:23:2]
+    be.ndfft(x, y, be.FftHandler(10), 1)
+    yo = np.zeros((4, 10), complex)
+    orc.ndfft(np.ascontiguousarray(x), yo, orc.FftHandler(10), 1)
+    assert orc.rel_l2(y, yo) < 1e-12
+    mask = np.ones(25, bool); mask[3:23:2] = False
+    assert np.all(out_base[:, mask] == 7 + 7j)
+
+
+def test_strided_views_device(dev):
+    be = dev.be
+    rng = np.random.default_rng(6)
+    base = rng.uniform(-1, 1, (64, 96))
+    t = torch.from_numpy(base).cuda()
+    x = t[::2, 1::3]                       # (32, 32) view, strides (192, 3)
+    y = torch.zeros((32, 17), dtype=torch.complex128, device="cuda")
+    be.ndfft_r2c(x, y, be.R2cFftHandler(32), 1)
+    yo = np.zeros((32, 17), complex)
+    orc.ndfft_r2c(base[::2, 1::3], yo, orc.R2cFftHandler(32), 1)
+    assert orc.rel_l2(y.cpu().numpy(), yo) < 1e-12
+    y0 = torch.zeros((17, 32), dtype=torch.complex128, device="cuda")
+    be.ndfft_r2c(x, y0, be.R2cFftHandler(32), 0)
+    orc_out = np.zeros((17, 32), complex)
+    orc.ndfft_r2c(base[::2, 1::3], orc_out, orc.R2cFftHandler(32), 0)
+    assert orc.rel_l2(y0.cpu().numpy(), orc_out) < 1e-12
+
+
+def test_custom_normalization_device(dev):
+    be = dev.be
+    Norm = type(be.FftHandler(4).norm)
+
+    def f(lane):
+        lane *= 0.25
+        lane[0] += 1.0
+
+    n = 16
+    rng = np.random.default_rng(2)
+    sp = rng.uniform(-1, 1, (3, n // 2 + 1)) + 1j * rng.uniform(-1, 1, (3, n // 2 + 1))
+    r = torch.zeros((3, n), dtype=torch.float64, device="cuda"); ro = np.zeros((3, n))
+    be.ndifft_r2c(torch.from_numpy(sp).cuda(), r, be.R2cFftHandler(n).normalization(Norm.Custom(f)), 1)
+    orc.ndifft_r2c(sp, ro, orc.R2cFftHandler(n).normalization(orc.Normalization.custom(f)), 1)
+    assert orc.rel_l2(r.cpu().numpy(), ro) < 1e-12
+    x = rng.uniform(-1, 1, (3, n)) + 1j * rng.uniform(-1, 1, (3, n))
+    y = torch.zeros((3, n), dtype=torch.complex128, device="cuda"); yo = np.zeros((3, n), complex)
+    be.ndifft(torch.from_numpy(x).cuda(), y, be.FftHandler(n).normalization(Norm.Custom(f)), 1)
+    orc.ndifft(x, yo, orc.FftHandler(n).normalization(orc.Normalization.custom(f)), 1)
+    assert orc.rel_l2(y.cpu().numpy(), yo) < 1e-12
+
+
+def test_errors(dev):
+    be = dev.be
+    h = be.FftHandler(6)
+    z = lambda *s: torch.zeros(s, dtype=torch.complex128, device="cuda")
+    with pytest.raises(AssertionError, match="Size mismatch in fft, got 5 expected 6"):
+        be.ndfft(z(2, 5), z(2, 5), h, 1)
+    with pytest.raises(AssertionError, match="Size mismatch in dct, got 5 expected 6"):
+        r = torch.zeros((5, 2), dtype=torch.float64, device="cuda")
+        be.nddct3(r, r.clone(), be.DctHandler(6), 0)
+    with pytest.raises(AssertionError):
+        be.ndfft(z(2, 6), z(3, 6), h, 1)
+    with pytest.raises(IndexError):
+        be.ndfft(z(2, 6), z(2, 6), h, 2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs at full size
+# ---------------------------------------------------------------------------------------------------
+def _rand(shape, rd, complex_, seed):
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    rt = TDT[np.dtype(rd)]
+    if complex_:
+        re = torch.rand(shape, generator=g, device="cuda", dtype=rt) * 2 - 1
+        im = torch.rand(shape, generator=g, device="cuda", dtype=rt) * 2 - 1
+        return torch.complex(re, im)
+    return torch.rand(shape, generator=g, device="cuda", dtype=rt) * 2 - 1
+
+
+def _lane_subset_check(be, op, n, x, y, axis, rd, nsample=48, seed=0):
+    """Compare `nsample` random lanes of the full-size result with the oracle."""
+    rng = np.random.default_rng(seed)
+    xm = torch.movedim(x, axis, -1).reshape(-1, x.shape[axis])
+    ym = torch.movedim(y, axis, -1).reshape(-1, y.shape[axis])
+    idx = torch.from_numpy(rng.choice(xm.shape[0], size=min(nsample, xm.shape[0]), replace=False)).cuda()
+    xs = xm[idx].cpu().numpy()
+    ys = ym[idx].cpu().numpy()
+    hk = Harness.OPS[op][0]
+    yo = np.zeros(ys.shape, np.complex128 if np.iscomplexobj(ys) else np.float64)
+    getattr(orc, op)(xs, yo, getattr(orc, hk)(n), 1)
+    err = orc.rel_l2(ys, yo)
+    assert err <= TOL[np.dtype(rd)], f"{op} n={n} axis={axis}: rel L2 {err:.3e}"
+    return err
+
+
+def _rel(a, b):
+    return float((torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b)).item())
+
+
+def test_config1_128x128_f64(dev):
+    # benches/ndrustfft.rs:9-60 shape: n x n f64, ramp data, axis 0; plus axis 1 and random data
+    n = 128
+    for axis in (0, 1):
+        for op in ("ndfft", "ndfft_r2c", "nddct2", "nddct1"):
+            dev.run(op, n, (n, n), axis, np.float64, seed=1)
+    be = dev.be
+    ramp = np.arange(n * n, dtype=np.float64).reshape(n, n)
+    y = torch.zeros((n, n), dtype=torch.complex128, device="cuda"); yo = np.zeros((n, n), complex)
+    be.ndfft_par(torch.from_numpy(ramp * (1 + 1j)).cuda(), y, be.FftHandler(n), 0)
+    orc.ndfft_par(ramp * (1 + 1j), yo, orc.FftHandler(n), 0)
+    assert orc.rel_l2(y.cpu().numpy(), yo) < 1e-12
+
+
+def test_config2_8192x8192_c64(dev):
+    be = dev.be
+    n = 8192
+    x = _rand((n, n), np.float32, True, 0xB200 + 32)
+    h = be.FftHandler(n, np.float32)
+    y = torch.empty_like(x); z = torch.empty_like(x)
+    for axis in (1, 0):
+        be.ndfft(x, y, h, axis)
+        _lane_subset_check(be, "ndfft", n, x, y, axis, np.float32, seed=axis)
+        be.ndifft(y, z, h, axis)
+        assert _rel(z, x) < 1e-5                       # round trip over the whole array
+        _lane_subset_check(be, "ndifft", n, y, z, axis, np.float32, seed=axis + 2)
+    # linearity on the whole array: F(a x + b x') = a F(x) + b F(x')
+    x2 = _rand((n, n), np.float32, True, 99)
+    be.ndfft(x2, z, h, 0)
+    be.ndfft(x, y, h, 0)
+    comb = 0.5 * x - 2.0 * x2
+    out = torch.empty_like(x)
+    be.ndfft(comb, out, h, 0)
+    assert _rel(out, 0.5 * y - 2.0 * z) < 1e-5
+
+
+def test_config3_512cubed_r2c_f64(dev):
+    be = dev.be
+    n = 512
+    x = _rand((n, n, n), np.float64, False, 0xB200 + 48)
+    hr = be.R2cFftHandler(n); hc = be.FftHandler(n)
+    a = torch.empty((n, n, n // 2 + 1), dtype=torch.complex128, device="cuda")
+    b = torch.empty_like(a); c = torch.empty_like(a)
+    be.ndfft_r2c(x, a, hr, 2)
+    _lane_subset_check(be, "ndfft_r2c", n, x, a, 2, np.float64)
+    be.ndfft(a, b, hc, 1)
+    _lane_subset_check(be, "ndfft", n, a, b, 1, np.float64)
+    be.ndfft(b, c, hc, 0)
+    _lane_subset_check(be, "ndfft", n, b, c, 0, np.float64)
+    # inverse chain returns the input (examples/rfft2.rs:49-53 pattern)
+    be.ndifft(c, b, hc, 0)
+    be.ndifft(b, a, hc, 1)
+    back = torch.empty_like(x)
+    be.ndifft_r2c(a, back, hr, 2)
+    assert _rel(back, x) < 1e-12
+    # checksum: DC bin of the 3-D spectrum equals the sum of the input
+    assert abs(c[0, 0, 0].real.item() - x.sum().item()) <= 1e-9 * n ** 3
+
+
+def test_config4_4096x4096_dct_f64(dev):
+    be = dev.be
+    n = 4096
+    x = _rand((n, n), np.float64, False, 0xB200 + 64)
+    h = be.DctHandler(n)
+    y = torch.empty_like(x); z = torch.empty_like(x)
+    for axis in (0, 1):
+        be.nddct2(x, y, h, axis)
+        _lane_subset_check(be, "nddct2", n, x, y, axis, np.float64, nsample=24)
+        be.nddct3(y, z, h, axis)
+        assert _rel(z, 2 * n * x) < 1e-12
+        _lane_subset_check(be, "nddct3", n, y, z, axis, np.float64, nsample=24)
+        be.nddct1(x, y, h, axis)
+        _lane_subset_check(be, "nddct1", n, x, y, axis, np.float64, nsample=24)
+        be.nddct1(y, z, h, axis)
+        assert _rel(z, 2 * (n - 1) * x) < 1e-12
+        be.nddct4(x, y, h, axis)
+        _lane_subset_check(be, "nddct4", n, x, y, axis, np.float64, nsample=24)
+        be.nddct4(y, z, h, axis)
+        assert _rel(z, 2 * n * x) < 1e-12
+
+
+def test_config5a_360x1000x384_c128(dev):
+    be = dev.be
+    shape = (360, 1000, 384)
+    x = _rand(shape, np.float64, True, 0xB200 + 80)
+    y = torch.empty_like(x); z = torch.empty_like(x)
+    for axis in (0, 1, 2):
+        h = be.FftHandler(shape[axis])
+        be.ndfft(x, y, h, axis)
+        _lane_subset_check(be, "ndfft", shape[axis], x, y, axis, np.float64, nsample=32)
+        be.ndifft(y, z, h, axis)
+        assert _rel(z, x) < 1e-12
+
+
+def test_config5a_bluestein_axis(dev):
+    # the named shape never triggers Bluestein; a 1009-long axis does (SURVEY.md 8d note)
+    be = dev.be
+    shape = (64, 1009, 48)
+    x = _rand(shape, np.float64, True, 5)
+    y = torch.empty_like(x); z = torch.empty_like(x)
+    h = be.FftHandler(1009)
+    assert h.describe()["ops"][0]["family"] == "bluestein"
+    be.ndfft(x, y, h, 1)
+    _lane_subset_check(be, "ndfft", 1009, x, y, 1, np.float64, nsample=32)
+    be.ndifft(y, z, h, 1)
+    assert _rel(z, x) < 1e-12
+
+
+@pytest.mark.parametrize("n,batch", [(1 << 16, 8), (1 << 20, 4), (3 * (1 << 18), 2)])
+def test_four_step_medium(dev, n, batch):
+    be = dev.be
+    x = _rand((batch, n), np.float32, True, n % 1000)
+    h = be.FftHandler(n, np.float32)
+    y = torch.empty_like(x); z = torch.empty_like(x)
+    be.ndfft(x, y, h, 1)
+    _lane_subset_check(be, "ndfft", n, x, y, 1, np.float32, nsample=2)
+    be.ndifft(y, z, h, 1)
+    assert _rel(z, x) < 1e-5
+    x64 = _rand((2, n), np.float64, True, 3)
+    h64 = be.FftHandler(n, np.float64)
+    y64 = torch.empty_like(x64)
+    be.ndfft(x64, y64, h64, 1)
+    _lane_subset_check(be, "ndfft", n, x64, y64, 1, np.float64, nsample=2)
+
+
+def test_config5b_2pow24_c64_batch64(dev):
+    be = dev.be
+    n, batch = 1 << 24, 64
+    x = _rand((batch, n), np.float32, True, 0xB200 + 81)
+    h = be.FftHandler(n, np.float32)
+    assert h.describe()["ops"][0]["family"] == "four-step"
+    y = torch.empty_like(x)
+    be.ndfft(x, y, h, 1)
+    _lane_subset_check(be, "ndfft", n, x, y, 1, np.float32, nsample=2)
+    # Parseval on the whole array: sum |X|^2 = n sum |x|^2
+    ex = torch.linalg.vector_norm(x).item() ** 2
+    ey = torch.linalg.vector_norm(y).item() ** 2
+    assert abs(ey / (n * ex) - 1) < 1e-4
+    back = torch.empty_like(x)
+    be.ndifft(y, back, h, 1)
+    assert _rel(back, x) < 1e-5
