@@ -362,8 +362,8 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
                           std::vector<BDim> dims, long long is_axis, long long os_axis, stream_t stream) {
     const size_t cs = sizeof(Cx<R>);
     const size_t cap = dev_smem_cap(p->device) - 1024;
-    const long long cap1 = (long long)(cap / (4 * cs + 64));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
-    const long long cap2 = (long long)(cap / (cs + 64));
+    const long long cap1 = (long long)((cap - 256) / (4 * cs));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
+    const long long cap2 = (long long)((cap - 256) / cs);
     if (!is_smooth(N)) return fail(NDFB_E_UNSUPPORTED, "length %lld has a prime factor > 13 and is too long for the single-pass Bluestein kernel", N);
     // N1 * N2 = N, N1 <= cap1, N2 <= cap2, as square as possible
     long long best1 = 0;
