@@ -2,28 +2,39 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 CSRC      := ndrustfft_b200/csrc
-SRCS      := $(CSRC)/ndfft_b200.cu
+SRCS      := $(CSRC)/ndfft_b200.cu $(CSRC)/sfft_inst_f32_rows.cu $(CSRC)/sfft_inst_f32_cols.cu $(CSRC)/sfft_inst_f64_rows.cu $(CSRC)/sfft_inst_f64_cols.cu
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/ndfft_b200.h
 LIBDIR    := ndrustfft_b200/lib
 LIB       := $(LIBDIR)/libndfft_b200.so
 EMULIB    := tests/emu/libndfft_b200_emu.so
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-fvisibility=hidden \
-             --expt-relaxed-constexpr -shared -cudart shared
-CXXFLAGS  := -O2 -g -std=c++17 -fPIC -shared -DNDFB_EMU -Itests/emu -x c++
+             --expt-relaxed-constexpr -cudart shared
+CXXFLAGS  := -O2 -g -std=c++17 -fPIC -DNDFB_EMU -Itests/emu
+OBJDIR    := build
+NVOBJS    := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/cuda/%.o,$(SRCS))
+EMUOBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/emu/%.o,$(SRCS))
 
 all: $(LIB) $(EMULIB)
 
 lib: $(LIB)
 emu: $(EMULIB)
 
-$(LIB): $(SRCS) $(HDRS)
-	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -o $@ $(SRCS)
+$(OBJDIR)/cuda/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)/cuda
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(EMULIB): $(SRCS) $(HDRS) tests/emu/simt_emu.h
-	$(CXX) $(CXXFLAGS) -o $@ $(SRCS)
+$(OBJDIR)/emu/%.o: $(CSRC)/%.cu $(HDRS) tests/emu/simt_emu.h
+	@mkdir -p $(OBJDIR)/emu
+	$(CXX) $(CXXFLAGS) -x c++ -c -o $@ $<
+
+$(LIB): $(NVOBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) -shared -cudart shared -gencode arch=compute_100a,code=sm_100a -o $@ $(NVOBJS)
+
+$(EMULIB): $(EMUOBJS)
+	$(CXX) -shared -o $@ $(EMUOBJS)
 
 clean:
-	rm -f $(LIB) $(EMULIB)
+	rm -rf $(LIB) $(EMULIB) $(OBJDIR)
 
 .PHONY: all lib emu clean

@@ -193,4 +193,61 @@ template <typename R> struct Dft<R, 7> : DftOdd<R, 7> {};
 template <typename R> struct Dft<R, 11> : DftOdd<R, 11> {};
 template <typename R> struct Dft<R, 13> : DftOdd<R, 13> {};
 
+// ---- radix 32 = 2 x 16 ----
+template <typename R>
+struct Dft<R, 32> {
+    static NDFB_DEV void run(Cx<R>* v) {
+        constexpr double wc[16] = {1.0, 0.9807852804032304491262, 0.9238795325112867561282, 0.8314696123025452370788,
+                                   0.7071067811865475244008, 0.5555702330196022247428, 0.3826834323650897717285,
+                                   0.1950903220161282678483, 0.0, -0.1950903220161282678483, -0.3826834323650897717285,
+                                   -0.5555702330196022247428, -0.7071067811865475244008, -0.8314696123025452370788,
+                                   -0.9238795325112867561282, -0.9807852804032304491262};
+        constexpr double ws[16] = {0.0, 0.1950903220161282678483, 0.3826834323650897717285, 0.5555702330196022247428,
+                                   0.7071067811865475244008, 0.8314696123025452370788, 0.9238795325112867561282,
+                                   0.9807852804032304491262, 1.0, 0.9807852804032304491262, 0.9238795325112867561282,
+                                   0.8314696123025452370788, 0.7071067811865475244008, 0.5555702330196022247428,
+                                   0.3826834323650897717285, 0.1950903220161282678483};
+        Cx<R> e[16], o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { e[j] = v[2 * j]; o[j] = v[2 * j + 1]; }
+        Dft<R, 16>::run(e);
+        Dft<R, 16>::run(o);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            Cx<R> t;
+            if (k == 0) t = o[0];
+            else if (k == 8) t = cmul_ni(o[8]);
+            else t = cmul(o[k], cmake<R>((R)wc[k], (R)-ws[k]));
+            v[k] = cadd(e[k], t);
+            v[k + 16] = csub(e[k], t);
+        }
+    }
+};
+
+// ---- radix 2B (B odd prime) = 2 x B Cooley-Tukey: used for 6 and 10 ----
+template <typename R, int B>
+struct DftTwiceOdd {
+    static NDFB_DEV void run(Cx<R>* v) {
+        Cx<R> e[B], o[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) { e[j] = v[2 * j]; o[j] = v[2 * j + 1]; }
+        Dft<R, B>::run(e);
+        Dft<R, B>::run(o);
+        v[0] = cadd(e[0], o[0]);
+        v[B] = csub(e[0], o[0]);
+#pragma unroll
+        for (int k = 1; k < B; ++k) {
+            // W_{2B}^k = exp(-i pi k / B) = -exp(-2 pi i ((k + B)/2) / B) for odd k, exp(-2 pi i (k/2) / B) for even k
+            R c, s;
+            if (k % 2 == 0) { c = (R)odd_cos<B>(k / 2); s = (R)odd_sin<B>(k / 2); }
+            else { c = -(R)odd_cos<B>((k + B) / 2); s = -(R)odd_sin<B>((k + B) / 2); }
+            Cx<R> t = cmul(o[k], cmake<R>(c, -s));
+            v[k] = cadd(e[k], t);
+            v[k + B] = csub(e[k], t);
+        }
+    }
+};
+template <typename R> struct Dft<R, 6> : DftTwiceOdd<R, 3> {};
+template <typename R> struct Dft<R, 10> : DftTwiceOdd<R, 5> {};
+
 }  // namespace ndfb

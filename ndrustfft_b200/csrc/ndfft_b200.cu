@@ -18,95 +18,17 @@
 
 #include "../../include/ndfft_b200.h"
 #include "common.h"
+#include "devapi.h"
 #include "plan.h"
+#include "sfft_inst.h"
 #include "tile_kernel.cuh"
 
 namespace ndfb {
 
-// ------------------------------------------------------------------------------------------------------
-// errors
-// ------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-
-static int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
-}
-
+std::string& err_slot() { return g_err; }
 static std::atomic<uint64_t> g_launches{0};
-
-// ------------------------------------------------------------------------------------------------------
-// device plumbing (CUDA, or plain host memory in the emulation build)
-// ------------------------------------------------------------------------------------------------------
-#ifdef NDFB_EMU
-typedef void* stream_t;
-static int dev_set(int) { return 0; }
-static int dev_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : NDFB_E_ALLOC; }
-static void dev_free(void* p) { std::free(p); }
-static int dev_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memcpy(d, h, bytes); return 0; }
-static int dev_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); return 0; }
-static int dev_sync(stream_t) { return 0; }
-static size_t dev_smem_cap(int) { return 227 * 1024; }
-static int dev_sm_count(int) { return 148; }
-template <typename K>
-static int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stream_t, const TileArgs& a) {
-    TileArgs copy = a;
-    simt::launch(dim3(grid), dim3(block), smem, [&]() { kernel(copy); });
-    g_launches++;
-    return 0;
-}
-static const char* kVersion = "ndfft_b200 0.1 emu (CPU SIMT emulation, tests only)";
-#else
-typedef cudaStream_t stream_t;
-static int cuda_fail(cudaError_t e, const char* what) {
-    return fail(NDFB_E_CUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
-}
-#define NDFB_CUDA(call)                                        \
-    do {                                                       \
-        cudaError_t e_ = (call);                               \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
-    } while (0)
-static int dev_set(int dev) { NDFB_CUDA(cudaSetDevice(dev)); return 0; }
-static int dev_malloc(void** p, size_t bytes) {
-    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(NDFB_E_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
-    return 0;
-}
-static void dev_free(void* p) { cudaFree(p); }
-static int dev_h2d(void* d, const void* h, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); return 0; }
-static int dev_d2h(void* h, const void* d, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); return 0; }
-static int dev_sync(stream_t s) { NDFB_CUDA(cudaStreamSynchronize(s)); return 0; }
-static size_t dev_smem_cap(int dev) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 227 * 1024; }
-    return (size_t)v;
-}
-static int dev_sm_count(int dev) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 148; }
-    return v;
-}
-template <typename K>
-static int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stream_t s, const TileArgs& a) {
-    static thread_local std::map<const void*, size_t> attr_set;
-    const void* key = (const void*)kernel;
-    auto it = attr_set.find(key);
-    if (it == attr_set.end() || it->second < smem) {
-        NDFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        attr_set[key] = 227 * 1024;
-    }
-    kernel<<<grid, block, smem, s>>>(a);
-    NDFB_CUDA(cudaGetLastError());
-    g_launches++;
-    return 0;
-}
-static const char* kVersion = "ndfft_b200 0.1 sm_100a";
-#endif
+std::atomic<uint64_t>& launch_counter() { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------------
 // plans
@@ -256,6 +178,32 @@ struct LaunchSpec {
     bool keep_dim_order = false;
 };
 
+// ---- fast path lookup ----
+static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes) {
+    static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
+    if (disabled) return nullptr;
+    const SfftEntry* tabs[4] = {kSfft_f32_rows, kSfft_f32_cols, kSfft_f64_rows, kSfft_f64_cols};
+    const int counts[4] = {kSfft_f32_rows_count, kSfft_f32_cols_count, kSfft_f64_rows_count, kSfft_f64_cols_count};
+    const int which = (f64 ? 2 : 0) + (cols ? 1 : 0);
+    const SfftEntry* best = nullptr;
+    for (int i = 0; i < counts[which]; ++i) {
+        const SfftEntry* e = &tabs[which][i];
+        if (e->N != N) continue;
+        if (!best) { best = e; continue; }
+        // prefer the widest tile that still lets two CTAs share an SM; never a tile much wider than the batch
+        const bool e_ok = e->smem <= 112 * 1024, b_ok = best->smem <= 112 * 1024;
+        const bool e_fit = e->L <= 2 * nlanes, b_fit = best->L <= 2 * nlanes;
+        if (e_fit != b_fit) { if (e_fit) best = e; continue; }
+        if (e_ok != b_ok) { if (e_ok) best = e; continue; }
+        if (e->L > best->L) best = e;
+    }
+    return best;
+}
+
+template <typename R>
+static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, stream_t stream);
+
+
 template <typename R>
 static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::string* describe = nullptr) {
     Core* c = s.core;
@@ -335,6 +283,47 @@ static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::
     return dev_launch(tile_kernel<R, false>, (unsigned)grid, (unsigned)T, smem, stream, a);
 }
 
+template <typename R>
+static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, stream_t stream) {
+    (void)p;
+    SfftArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.in = s.in; a.out = s.out;
+    long long nlanes = 1;
+    for (auto& d : s.dims) nlanes *= d.size;
+    if (nlanes == 0) return 0;
+    a.nlanes = nlanes;
+    a.nbd = (int)s.dims.size();
+    for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
+    a.is_axis = s.is_axis; a.os_axis = s.os_axis;
+    a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
+    a.tw = s.core->d.tw;
+    a.fs_twiddle = s.fs_twiddle; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
+    const long long grid = (nlanes + e->L - 1) / e->L;
+    if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+    return e->launch(a, (unsigned)grid, stream);
+}
+
+// C2C launch: the instantiated Stockham schedule when there is one, else the general tile kernel
+template <typename R>
+static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
+    const CoreTables& t = s.core->t;
+    if (t.kind == TK_C2C && t.M == 0 && (int)s.dims.size() <= kMaxBatchDims) {
+        long long nlanes = 1;
+        for (auto& d : s.dims) nlanes *= d.size;
+        const bool have_batch = !s.dims.empty() && nlanes > 1;
+        const bool cols = have_batch && t.N > 1 &&
+                          (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
+        const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes);
+        if (e) {
+            static const bool trace = std::getenv("NDFB_TRACE") != nullptr;
+            if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
+            return launch_sfft<R>(p, e, s, stream);
+        }
+    }
+    return launch_tile<R>(p, s, stream);
+}
+
 // order batch dims by input stride and merge the ones that are contiguous in both arrays
 static void normalize_dims(std::vector<BDim>& dims) {
     std::vector<BDim> v;
@@ -399,7 +388,7 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     for (auto& d : dims) { s1.dims.push_back({d.size, d.is, wstride}); wstride *= d.size; }
     s1.is_axis = N2 * is_axis; s1.os_axis = N2;
     s1.conj_in = inverse; s1.fs_twiddle = 1; s1.fs = fs;
-    if ((rc = launch_tile<R>(p, s1, stream))) return rc;
+    if ((rc = launch_c2c<R>(p, s1, stream))) return rc;
     // pass 2: lanes (k1, batch...), transform over j2 (contiguous), out[k1 + N1*k2]
     LaunchSpec s2;
     s2.core = c2; s2.in = ws; s2.out = out;
@@ -408,7 +397,7 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     for (auto& d : dims) { s2.dims.push_back({d.size, wstride, d.os}); wstride *= d.size; }
     s2.is_axis = 1; s2.os_axis = N1 * os_axis;
     s2.conj_out = inverse; s2.scale = scale;
-    return launch_tile<R>(p, s2, stream);
+    return launch_c2c<R>(p, s2, stream);
 }
 
 struct OpInfo {
@@ -516,14 +505,14 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
             s.core = c; s.in = (const char*)in + io * (long long)ie; s.out = (char*)out + oo * (long long)oe;
             s.dims = inner; s.is_axis = is_axis; s.os_axis = os_axis;
             s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-            if ((rc = launch_tile<R>(p, s, stream))) return rc;
+            if ((rc = launch_c2c<R>(p, s, stream))) return rc;
         }
         return 0;
     }
     LaunchSpec s;
     s.core = c; s.in = in; s.out = out; s.dims = dims; s.is_axis = is_axis; s.os_axis = os_axis;
     s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-    return launch_tile<R>(p, s, stream);
+    return launch_c2c<R>(p, s, stream);
 }
 
 // byte span [lo, hi) touched by a strided array, relative to its base pointer
@@ -684,7 +673,7 @@ size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {
 }
 
 const char* ndfb_last_error(void) { return g_err.c_str(); }
-const char* ndfb_version(void) { return kVersion; }
+const char* ndfb_version(void) { return version_string(); }
 uint64_t ndfb_launch_count(void) { return g_launches.load(); }
 void ndfb_release_workspaces(void) { g_pool.release(); }
 

@@ -167,3 +167,41 @@ def test_four_step_decomposition_small(hs):
         hs.run("ndifft", 36, (2, 36, 2), 1, np.float32, seed=8)
     finally:
         del os.environ["NDFB_FORCE_FOUR_STEP"]
+
+
+# ---- the instantiated Stockham fast path (sfft_kernel.cuh): every registered length, both layouts ----
+SFFT_SIZES = [64, 128, 256, 512, 1024, 2048, 4096, 8192, 36, 60, 100, 216, 360, 384, 600, 1000]
+
+
+@pytest.mark.parametrize("n", SFFT_SIZES)
+def test_sfft_registered_lengths(hs, n, capfd):
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run("ndfft", n, (3, n), 1, np.float64, seed=n)
+        hs.run("ndifft", n, (n, 5), 0, np.float64, seed=n + 1)
+        hs.run("ndifft", n, (2, n), 1, np.float32, seed=n + 2)
+        hs.run("ndfft", n, (n, 9), 0, np.float32, seed=n + 3)
+        hs.run("ndfft", n, (2, n, 3), 1, np.float32, norm="none", seed=n + 4)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    # the fast path, not the general kernel, ran (f64 8192 strided columns have no schedule: 139 KB x 2 lanes)
+    assert err.count("[ndfb] sfft") == (4 if n == 8192 else 5), err
+
+
+def test_sfft_and_general_kernel_agree(hs):
+    """Same inputs through both kernel families (NDFB_DISABLE_SFFT is read once per process, so compare via oracle)."""
+    hs.run("ndfft", 16384, (1, 16384), 1, np.float32, seed=1)     # f32 16384 has no schedule: general kernel
+    hs.run("ndfft", 8192, (1, 8192), 1, np.float32, seed=1)       # fast path
+
+
+def test_four_step_through_fast_path(hs):
+    import os
+    os.environ["NDFB_FORCE_FOUR_STEP"] = "1"
+    try:
+        hs.run("ndfft", 4096, (2, 4096), 1, np.float32, seed=5)      # 64 x 64, both passes on sfft schedules
+        hs.run("ndifft", 8192, (2, 8192), 1, np.float64, seed=6)     # 64 x 128
+        hs.run("ndfft", 4096, (4096, 3), 0, np.float64, seed=7)
+    finally:
+        del os.environ["NDFB_FORCE_FOUR_STEP"]
