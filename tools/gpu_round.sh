@@ -1,9 +1,15 @@
+#!/bin/bash
+# One GPU session: smoke, parity tests, bench, config sweep, ncu launch list + full capture of the bench kernels.
+TAG=${1:-r1}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt; free -g | head -2 >> gpurun_out/gpu.txt
+nproc >> gpurun_out/gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+if [ -z "$SKIP_TESTS" ]; then
 timeout 1800 python -m pytest tests -m gpu -q --maxfail=40 --timeout 900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_kernel -s 4 -c 4 -o gpurun_out/prof_r1a python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
-tail -5 gpurun_out/smoke.log; tail -15 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+fi
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 900 python tools/bench_configs.py ${SWEEP_ARGS} > gpurun_out/configs_$TAG.jsonl 2> gpurun_out/configs.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sfft_kernel|tile_kernel' -s 4 -c 4 -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/smoke.log; tail -12 gpurun_out/pytest_gpu.log 2>/dev/null; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench.err; cat gpurun_out/configs_$TAG.jsonl; tail -5 gpurun_out/configs.err
