@@ -2,8 +2,8 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 CSRC      := ndrustfft_b200/csrc
-SRCS      := $(CSRC)/ndfft_b200.cu $(CSRC)/sfft_inst_f32_rows.cu $(CSRC)/sfft_inst_f32_cols.cu $(CSRC)/sfft_inst_f64_rows.cu $(CSRC)/sfft_inst_f64_cols.cu
-HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/ndfft_b200.h
+SRCS      := $(CSRC)/ndfft_b200.cu $(sort $(wildcard $(CSRC)/sfft_inst_*.cu) $(wildcard $(CSRC)/rsfft_inst_*.cu))
+HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh $(CSRC)/*.inc) include/ndfft_b200.h
 LIBDIR    := ndrustfft_b200/lib
 LIB       := $(LIBDIR)/libndfft_b200.so
 EMULIB    := tests/emu/libndfft_b200_emu.so

@@ -38,6 +38,7 @@ struct DeviceTables {
     uint32_t* perm = nullptr;
     void *fs_lo = nullptr, *fs_hi = nullptr;
     bool ready = false;
+    std::map<uint32_t, void*> sfft_tw;  // per-pass Stockham twiddle tables, keyed by the radix schedule
 };
 
 struct Core {
@@ -283,9 +284,34 @@ static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::
     return dev_launch(tile_kernel<R, false>, (unsigned)grid, (unsigned)T, smem, stream, a);
 }
 
+// W_{P r}^{q k} for every pass p >= 1 of the schedule, in Sched::twoff layout
+template <typename R>
+static int get_sfft_twiddles(ndfb_plan* p, Core* c, const SfftEntry* e, void** out) {
+    std::lock_guard<std::mutex> g(c->mu);
+    const uint32_t key = (uint32_t)e->r[0] | ((uint32_t)e->r[1] << 8) | ((uint32_t)e->r[2] << 16) | ((uint32_t)e->r[3] << 24);
+    auto it = c->d.sfft_tw.find(key);
+    if (it != c->d.sfft_tw.end()) { *out = it->second; return 0; }
+    std::vector<cld> t;
+    long long P = e->r[0];
+    for (int ps = 1; ps < 4 && e->r[ps] > 1; ++ps) {
+        const int r = e->r[ps];
+        for (int q = 1; q < r; ++q)
+            for (long long k = 0; k < P; ++k) t.push_back(unit_root((long long)q * k, P * r));
+        P *= r;
+    }
+    if ((int)t.size() != e->twtotal) return fail(NDFB_E_INVALID, "internal: twiddle table size mismatch (%zu vs %d)", t.size(), e->twtotal);
+    if (t.empty()) t.push_back(cld(1, 0));
+    void* d = nullptr;
+    int rc = dev_set(p->device);
+    if (rc) return rc;
+    if ((rc = upload_cx<R>(&d, t))) return rc;
+    c->d.sfft_tw[key] = d;
+    *out = d;
+    return 0;
+}
+
 template <typename R>
 static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, stream_t stream) {
-    (void)p;
     SfftArgs a;
     std::memset(&a, 0, sizeof a);
     a.in = s.in; a.out = s.out;
@@ -297,7 +323,12 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
     a.is_axis = s.is_axis; a.os_axis = s.os_axis;
     a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
-    a.tw = s.core->d.tw;
+    {
+        void* twd = nullptr;
+        int rc = get_sfft_twiddles<R>(p, s.core, e, &twd);
+        if (rc) return rc;
+        a.tw = twd;
+    }
     a.fs_twiddle = s.fs_twiddle; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
     const long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
@@ -316,9 +347,92 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
                           (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
         const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes);
         if (e) {
-            static const bool trace = std::getenv("NDFB_TRACE") != nullptr;
+            const bool trace = std::getenv("NDFB_TRACE") != nullptr;
             if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
             return launch_sfft<R>(p, e, s, stream);
+        }
+    }
+    return launch_tile<R>(p, s, stream);
+}
+
+// ---- real-transform fast path ----
+static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long long nlanes) {
+    static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
+    if (disabled) return nullptr;
+    struct Tab { const RsfftEntry* e; int n; };
+#define RSFFT_TABLE(name) {kRsfft_##name, kRsfft_##name##_count},
+    static const Tab tabs[] = {
+#include "rsfft_tables.inc"
+    };
+#undef RSFFT_TABLE
+    const RsfftEntry* best = nullptr;
+    for (const Tab& t : tabs)
+        for (int i = 0; i < t.n; ++i) {
+            const RsfftEntry* e = &t.e[i];
+            if (e->f64 != (f64 ? 1 : 0) || e->kind != rkind || e->N != N || e->cols != (cols ? 1 : 0)) continue;
+            if (!best || (e->L <= 2 * nlanes && e->L > best->L)) best = e;
+        }
+    return best;
+}
+
+// The even-length real kinds: TileKind -> RKind of rsfft_kernel (odd lengths stay on the general kernel)
+static int rkind_of(int tk) {
+    switch (tk) {
+        case TK_R2C_EVEN: return RK_R2C;
+        case TK_C2R_EVEN: return RK_C2R;
+        case TK_DCT1: return RK_DCT1;
+        case TK_DCT2_EVEN: return RK_DCT2;
+        case TK_DCT3_EVEN: return RK_DCT3;
+        case TK_DCT4_EVEN: return RK_DCT4;
+        default: return -1;
+    }
+}
+
+template <typename R>
+static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
+    const CoreTables& t = s.core->t;
+    const int rk = rkind_of(t.kind);
+    if (rk >= 0 && t.M == 0 && t.N >= 2 && (int)s.dims.size() <= kMaxBatchDims) {
+        long long nlanes = 1;
+        for (auto& d : s.dims) nlanes *= d.size;
+        const bool have_batch = !s.dims.empty() && nlanes > 1;
+        const bool cols = have_batch && (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
+        // the row kernels read / write (re, im)-style pairs of reals with one vector access: needs pair alignment
+        bool ok = true;
+        if (!cols) {
+            if (rk == RK_R2C && s.is_axis == 1) {
+                ok = ((uintptr_t)s.in % (2 * sizeof(R))) == 0;
+                for (auto& d : s.dims) if (d.is % 2) ok = false;
+            }
+            if (rk == RK_C2R && s.os_axis == 1) {
+                ok = ((uintptr_t)s.out % (2 * sizeof(R))) == 0;
+                for (auto& d : s.dims) if (d.os % 2) ok = false;
+            }
+        }
+        const RsfftEntry* e = ok ? find_rsfft(sizeof(R) == 8, rk, t.N, cols, nlanes) : nullptr;
+        if (e) {
+            const bool trace = std::getenv("NDFB_TRACE") != nullptr;
+            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
+            RsfftArgs a;
+            std::memset(&a, 0, sizeof a);
+            a.in = s.in; a.out = s.out; a.nlanes = nlanes;
+            if (nlanes == 0) return 0;
+            a.nbd = (int)s.dims.size();
+            for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
+            a.is_axis = s.is_axis; a.os_axis = s.os_axis;
+            a.n = t.n; a.scale = s.scale;
+            a.tabA = s.core->d.tabA; a.tabB = s.core->d.tabB;
+            SfftEntry proxy;
+            std::memset(&proxy, 0, sizeof proxy);
+            for (int i = 0; i < 4; ++i) proxy.r[i] = e->r[i];
+            proxy.twtotal = e->twtotal;
+            void* twd = nullptr;
+            int rc = get_sfft_twiddles<R>(p, s.core, &proxy, &twd);
+            if (rc) return rc;
+            a.tw = twd;
+            const long long grid = (nlanes + e->L - 1) / e->L;
+            if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+            return e->launch(a, (unsigned)grid, stream);
         }
     }
     return launch_tile<R>(p, s, stream);
@@ -505,14 +619,14 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
             s.core = c; s.in = (const char*)in + io * (long long)ie; s.out = (char*)out + oo * (long long)oe;
             s.dims = inner; s.is_axis = is_axis; s.os_axis = os_axis;
             s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-            if ((rc = launch_c2c<R>(p, s, stream))) return rc;
+            if ((rc = (o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream)))) return rc;
         }
         return 0;
     }
     LaunchSpec s;
     s.core = c; s.in = in; s.out = out; s.dims = dims; s.is_axis = is_axis; s.os_axis = os_axis;
     s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-    return launch_c2c<R>(p, s, stream);
+    return o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream);
 }
 
 // byte span [lo, hi) touched by a strided array, relative to its base pointer
@@ -586,6 +700,7 @@ void ndfb_plan_destroy(ndfb_plan* p) {
         DeviceTables& d = kv.second->d;
         void* ptrs[] = {d.tw, d.tabA, d.tabB, d.blu_c, d.blu_bhat, d.perm};
         for (void* q : ptrs) if (q) dev_free(q);
+        for (auto& kv2 : d.sfft_tw) if (kv2.second) dev_free(kv2.second);
     }
     for (auto& kv : p->fs) { if (kv.second.lo) dev_free(kv.second.lo); if (kv.second.hi) dev_free(kv.second.hi); }
     delete p;

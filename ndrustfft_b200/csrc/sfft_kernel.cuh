@@ -7,7 +7,7 @@
 //   * between passes the points are exchanged through shared memory in Stockham autosort order
 //     (write Y[(b-k) r + k + q P], read X[i + TL e]); with P passes that is P-1 exchanges, each
 //     bank-conflict free thanks to one pad element per r0 points;
-//   * twiddles come from one table W_N^t in global memory (L1/L2 resident);
+//   * twiddles come from per-pass tables laid out k-fastest so a warp's loads are coalesced (L1/L2 resident);
 //   * inverse transforms are conj-in / conj-out of the forward schedule; 1/n (Normalization::Default,
 //     src/lib.rs:333-338) and the four-step inter-pass twiddle are fused into the store.
 // Replaces fft_lane / ifft_lane (src/lib.rs:313-331) plus the lane loop and copies of src/lib.rs:119-163.
@@ -26,7 +26,7 @@ struct SfftArgs {
     long long is_axis, os_axis;
     int conj_in, conj_out;
     double scale;
-    const void* tw;  // W_N^t, t < N
+    const void* tw;  // per-pass twiddle tables in Sched::twoff layout
     int fs_twiddle, fs_shift;
     const void* fs_lo;
     const void* fs_hi;
@@ -45,6 +45,12 @@ struct Sched {
     static constexpr int nbf(int p) { return N_ / radix(p); }                   // butterflies per lane in pass p
     static constexpr int G(int p) { return (nbf(p) + TL_ - 1) / TL_; }          // butterflies per thread
     static constexpr int EP(int p) { return p < NP ? G(p) * radix(p) : 0; }
+    // per-pass twiddle tables, concatenated: pass p >= 1 holds W_{P r}^{q k} at twoff(p) + (q-1) P + k  (k < P fastest,
+    // so the 32 lanes of a warp, which hold consecutive butterflies b and therefore consecutive k = b mod P, read
+    // consecutive addresses)
+    static constexpr int twsize(int p) { return (p >= 1 && p < NP) ? (radix(p) - 1) * before(p) : 0; }
+    static constexpr int twoff(int p) { return p <= 1 ? 0 : twoff(p - 1) + twsize(p - 1); }
+    static constexpr int TWTOTAL = twsize(1) + twsize(2) + twsize(3);
     static constexpr int E = cmax(cmax(EP(0), EP(1)), cmax(EP(2), EP(3)));      // register slots per thread
     // one pad element per R0 points keeps the stride-R0 writes of pass 0 off a single bank
     static constexpr int pad(int a) { return a + a / R0_; }
@@ -54,9 +60,6 @@ struct Sched {
 template <typename R, class S, int L, bool COLS>
 struct SfftCtx {
     Cx<R>* smem;
-    const Cx<R>* in;
-    Cx<R>* out;
-    long long is_axis, os_axis;
     int i, l;  // position within the lane group, lane within the tile
     bool valid;
     NDFB_DEV int addr(int a) const {
@@ -67,8 +70,10 @@ struct SfftCtx {
 
 // One Stockham pass.  Butterfly b of this pass (b < N/r) reads X[b + q N/r], multiplies by W_{P r}^{q k}
 // (k = b mod P, P = product of the earlier radices) and writes Y[(b-k) r + k + q P].
-// Pass 0 reads global memory, the last pass writes global memory (both coalesced in b).
-template <typename R, class S, int L, bool COLS, int PASS>
+// Pass 0 takes its inputs from `load(j)` (global memory, coalesced in b), the last pass hands its outputs to
+// `store(k, value)`.  SYNC0 / SYNCL add a barrier after the loads of the first / last pass for callers whose
+// load or store functor itself goes through the shared buffer (staged rows, pair epilogues).
+template <typename R, class S, int L, bool COLS, int PASS, bool SYNC0, bool SYNCL>
 struct SfftPass {
     static constexpr int r = S::radix(PASS);
     static constexpr int P = S::before(PASS);
@@ -78,35 +83,31 @@ struct SfftPass {
     static constexpr bool LAST = PASS == S::NP - 1;
     static constexpr bool FULL = (NB % S::TL) == 0;  // no idle threads in this pass
 
-    template <typename StoreF>
+    template <typename LoadF, typename StoreF>
     static NDFB_DEV void run(const SfftCtx<R, S, L, COLS>& c, Cx<R> (&v)[S::E], const Cx<R>* __restrict__ tw,
-                             const SfftArgs& a, StoreF store) {
+                             LoadF load, StoreF store) {
 #pragma unroll
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
             if (FULL || b < NB) {
 #pragma unroll
                 for (int q = 0; q < r; ++q) {
-                    if (FIRST) {
-                        Cx<R> x = c.valid ? c.in[(long long)(b + q * NB) * c.is_axis] : cmake<R>((R)0, (R)0);
-                        if (a.conj_in) x.y = -x.y;
-                        v[m * r + q] = x;
-                    } else {
-                        v[m * r + q] = c.smem[c.addr(b + q * NB)];
-                    }
+                    if (FIRST) v[m * r + q] = load(b + q * NB);
+                    else v[m * r + q] = c.smem[c.addr(b + q * NB)];
                 }
             }
         }
-        if (!FIRST && !LAST) __syncthreads();  // every thread has read the previous layout before it is overwritten
+        // every thread has read the previous layout before it is overwritten
+        if ((!FIRST && !LAST) || (FIRST && SYNC0 && !LAST) || (LAST && SYNCL)) __syncthreads();
 #pragma unroll
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
             if (FULL || b < NB) {
                 const int k = b % P;
                 if (!FIRST) {
-                    constexpr int step = S::N / (P * r);
+                    const Cx<R>* __restrict__ twp = tw + S::twoff(PASS) + k;
 #pragma unroll
-                    for (int q = 1; q < r; ++q) v[m * r + q] = cmul(v[m * r + q], ldg(&tw[q * k * step]));
+                    for (int q = 1; q < r; ++q) v[m * r + q] = cmul(v[m * r + q], ldg(&twp[(q - 1) * P]));
                 }
                 Dft<R, r>::run(&v[m * r]);
                 if (LAST) {
@@ -122,15 +123,43 @@ struct SfftPass {
     }
 };
 
-template <typename R, class S, int L, bool COLS, int PASS>
+template <typename R, class S, int L, bool COLS, int PASS, bool SYNC0, bool SYNCL>
 struct SfftAll {
-    template <typename StoreF>
-    static NDFB_DEV void run(const SfftCtx<R, S, L, COLS>& c, Cx<R> (&v)[S::E], const Cx<R>* tw, const SfftArgs& a, StoreF store) {
-        SfftPass<R, S, L, COLS, PASS>::run(c, v, tw, a, store);
-        if constexpr (PASS + 1 < S::NP) SfftAll<R, S, L, COLS, PASS + 1>::run(c, v, tw, a, store);
+    template <typename LoadF, typename StoreF>
+    static NDFB_DEV void run(const SfftCtx<R, S, L, COLS>& c, Cx<R> (&v)[S::E], const Cx<R>* tw, LoadF load, StoreF store) {
+        SfftPass<R, S, L, COLS, PASS, SYNC0, SYNCL>::run(c, v, tw, load, store);
+        if constexpr (PASS + 1 < S::NP) SfftAll<R, S, L, COLS, PASS + 1, SYNC0, SYNCL>::run(c, v, tw, load, store);
     }
 };
 
+// lane -> global base offsets (elements of the respective array); also the index along the fastest batch dim
+struct LaneBase {
+    long long bi, bo;
+    int j2;
+};
+template <typename A>
+NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid) {
+    LaneBase o;
+    o.bi = 0; o.bo = 0; o.j2 = 0;
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < kMaxBatchDims; ++d) {
+            if (d < a.nbd) {
+                const long long q = g / a.bsz[d];
+                const long long rr = g - q * a.bsz[d];
+                if (d == 0) o.j2 = (int)rr;
+                o.bi += rr * a.bis[d];
+                o.bo += rr * a.bos[d];
+                g = q;
+            }
+        }
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// complex-to-complex
+// ------------------------------------------------------------------------------------------------------
 template <typename R, class S, int L, bool COLS, int MINB>
 __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_constant__ SfftArgs a) {
     NDFB_DYN_SMEM(smem_raw);
@@ -139,34 +168,26 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     const int tid = threadIdx.x;
     if (COLS) { c.l = tid % L; c.i = tid / L; }
     else { c.i = tid % S::TL; c.l = tid / S::TL; }
-    // this thread's lane in the global arrays
-    long long g = (long long)blockIdx.x * L + c.l;
+    const long long g = (long long)blockIdx.x * L + c.l;
     c.valid = g < a.nlanes;
-    long long bi = 0, bo = 0;
-    int j2 = 0;
-    if (c.valid) {
-#pragma unroll
-        for (int d = 0; d < kMaxBatchDims; ++d) {
-            if (d < a.nbd) {
-                const long long q = g / a.bsz[d];
-                const long long rr = g - q * a.bsz[d];
-                if (d == 0) j2 = (int)rr;
-                bi += rr * a.bis[d];
-                bo += rr * a.bos[d];
-                g = q;
-            }
-        }
-    }
-    c.in = reinterpret_cast<const Cx<R>*>(a.in) + bi;
-    c.out = reinterpret_cast<Cx<R>*>(a.out) + bo;
-    c.is_axis = a.is_axis;
-    c.os_axis = a.os_axis;
+    const LaneBase lb = lane_base(a, g, c.valid);
+    const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
+    Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
+    const long long is_axis = a.is_axis, os_axis = a.os_axis;
     const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
     const R sc = (R)a.scale;
     const R sy = a.conj_out ? -sc : sc;
+    const bool cj = a.conj_in != 0;
+    const bool valid = c.valid;
+    const int j2 = lb.j2;
     Cx<R> v[S::E];
+    auto load = [&](int j) -> Cx<R> {
+        Cx<R> x = valid ? in[(long long)j * is_axis] : cmake<R>((R)0, (R)0);
+        if (cj) x.y = -x.y;
+        return x;
+    };
     auto store = [&](int k, Cx<R> val) {
-        if (!c.valid) return;
+        if (!valid) return;
         Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
         if (a.fs_twiddle) {
             const Cx<R>* lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
@@ -174,9 +195,173 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
             const unsigned long long ee = (unsigned long long)k * (unsigned long long)j2;
             y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
         }
-        c.out[(long long)k * c.os_axis] = y;
+        out[(long long)k * os_axis] = y;
     };
-    SfftAll<R, S, L, COLS, 0>::run(c, v, tw, a, store);
+    SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// real transforms of even length around the same Stockham core of N = n/2 (DCT-I: N = n-1) complex points:
+// R2C, C2R, DCT-I..IV.  The algebra is the one verified in tests/kernel_math_model.py and used by
+// tile_kernel.cuh; here it is fused into the first-pass loads and the last-pass stores:
+//   * strided columns (COLS): every real load/store is coalesced across the L adjacent lanes whatever the
+//     row order, so reorders (Makhoul, even extension, zip) cost nothing;
+//   * contiguous rows: kinds whose access along the row is strided (DCT-II in, DCT-III out, DCT-IV in/out)
+//     are staged through the shared buffer with coalesced copies.
+// Replaces fft_r2c_lane / ifft_r2c_lane (src/lib.rs:497-523) and dct1..4_lane (src/lib.rs:688-734).
+// ------------------------------------------------------------------------------------------------------
+enum RKind : int { RK_R2C = 0, RK_C2R = 1, RK_DCT1 = 2, RK_DCT2 = 3, RK_DCT3 = 4, RK_DCT4 = 5 };
+
+struct RsfftArgs {
+    const void* in;
+    void* out;
+    long long nlanes;
+    int nbd;
+    long long bsz[kMaxBatchDims], bis[kMaxBatchDims], bos[kMaxBatchDims];
+    long long is_axis, os_axis;
+    int n;            // logical (real) length
+    double scale;
+    const void* tw;   // per-pass twiddle tables
+    const void* tabA; // exp(-2 pi i k / (2N)), k <= N   (DCT-IV: exp(-i pi j / n))
+    const void* tabB; // DCT-II/III: exp(-i pi k / (2n));  DCT-IV: exp(-i pi (4j+1) / (4n))
+};
+
+template <typename R, class S, int L, bool COLS, int KIND, int MINB>
+__global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_constant__ RsfftArgs a) {
+    constexpr int N = S::N;
+    constexpr bool IN_CX = KIND == RK_C2R;
+    constexpr bool OUT_CX = KIND == RK_R2C;
+    // which sides need the coalesced staging copy when the lane is a contiguous row
+    constexpr bool STAGE_IN = !COLS && (KIND == RK_DCT2 || KIND == RK_DCT4);
+    constexpr bool STAGE_OUT = !COLS && (KIND == RK_DCT3 || KIND == RK_DCT4);
+    constexpr bool PAIR_EPI = KIND == RK_R2C || KIND == RK_DCT1 || KIND == RK_DCT2;   // outputs need Z[k] and Z[N-k]
+    NDFB_DYN_SMEM(smem_raw);
+    SfftCtx<R, S, L, COLS> c;
+    c.smem = reinterpret_cast<Cx<R>*>(smem_raw);
+    R* smem_r = reinterpret_cast<R*>(smem_raw);
+    const int tid = threadIdx.x;
+    if (COLS) { c.l = tid % L; c.i = tid / L; }
+    else { c.i = tid % S::TL; c.l = tid / S::TL; }
+    const long long g = (long long)blockIdx.x * L + c.l;
+    c.valid = g < a.nlanes;
+    const bool valid = c.valid;
+    const LaneBase lb = lane_base(a, g, valid);
+    const R* __restrict__ in_r = reinterpret_cast<const R*>(a.in) + (IN_CX ? 2 * lb.bi : lb.bi);
+    const Cx<R>* __restrict__ in_c = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
+    R* __restrict__ out_r = reinterpret_cast<R*>(a.out) + (OUT_CX ? 2 * lb.bo : lb.bo);
+    Cx<R>* __restrict__ out_c = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
+    const long long is_axis = a.is_axis, os_axis = a.os_axis;
+    const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
+    const Cx<R>* __restrict__ tabA = reinterpret_cast<const Cx<R>*>(a.tabA);
+    const Cx<R>* __restrict__ tabB = reinterpret_cast<const Cx<R>*>(a.tabB);
+    const int n = a.n;
+    const R sc = (R)a.scale;
+    const R zero = (R)0;
+    // staged real lane in shared memory (rows only): real index t of lane l
+    constexpr int RPITCH = 2 * S::NPAD;
+    auto sreal = [&](int t) -> R& { return smem_r[c.l * RPITCH + t]; };
+    auto gin = [&](int t) -> R { return valid ? in_r[(long long)t * is_axis] : zero; };          // real input element t
+    auto xin = [&](int t) -> R { return STAGE_IN ? sreal(t) : gin(t); };
+
+    if (STAGE_IN) {
+        for (int t = c.i; t < n; t += S::TL) sreal(t) = gin(t);
+        __syncthreads();
+    }
+
+    // ---- first-pass input z[j], j < N ----
+    auto load = [&](int j) -> Cx<R> {
+        if (KIND == RK_R2C) {
+            if (!COLS && is_axis == 1) {   // (x[2j], x[2j+1]) is one aligned complex load
+                return valid ? reinterpret_cast<const Cx<R>*>(in_r)[j] : cmake<R>(zero, zero);
+            }
+            return cmake<R>(gin(2 * j), gin(2 * j + 1));
+        } else if (KIND == RK_C2R || KIND == RK_DCT3) {
+            Cx<R> xk, xn;
+            const int k2 = N - j;
+            if (KIND == RK_C2R) {
+                xk = valid ? in_c[(long long)j * is_axis] : cmake<R>(zero, zero);
+                xn = valid ? in_c[(long long)k2 * is_axis] : cmake<R>(zero, zero);
+                if (j == 0) { xk.y = zero; xn.y = zero; }        // Im X[0], Im X[N] dropped (src/lib.rs:516-521)
+            } else {
+                // P[k] = (y[k], -y[n-k]) with y[n] = 0, then V[k] = conj(t_k) P[k]
+                Cx<R> pk = cmake<R>(gin(j), j == 0 ? zero : -gin(n - j));
+                Cx<R> pn = cmake<R>(gin(k2), -gin(n - k2));
+                xk = cmul(pk, cconj(ldg(&tabB[j])));
+                xn = cmul(pn, cconj(ldg(&tabB[k2])));
+            }
+            const Cx<R> wc = cconj(ldg(&tabA[j]));
+            const Cx<R> E = cadd(xk, cconj(xn)), O = csub(xk, cconj(xn));
+            return cconj(cadd(E, cmul_i(cmul(wc, O))));
+        } else if (KIND == RK_DCT1) {
+            // even extension e[t] = x[t] (t <= N), x[2N - t] otherwise; z[j] = (e[2j], e[2j+1])
+            const int t0 = 2 * j, t1 = 2 * j + 1;
+            return cmake<R>(gin(t0 <= N ? t0 : 2 * N - t0), gin(t1 <= N ? t1 : 2 * N - t1));
+        } else if (KIND == RK_DCT2) {
+            // Makhoul: v[t] = x[2t] (t < N) else x[2(n-1-t)+1]; z[j] = (v[2j], v[2j+1])
+            const int t0 = 2 * j, t1 = 2 * j + 1;
+            return cmake<R>(xin(t0 < N ? 2 * t0 : 2 * (n - 1 - t0) + 1), xin(t1 < N ? 2 * t1 : 2 * (n - 1 - t1) + 1));
+        } else {  // RK_DCT4
+            return cmul(cmake<R>(xin(2 * j), xin(n - 1 - 2 * j)), ldg(&tabA[j]));
+        }
+    };
+
+    // ---- last-pass output ----
+    auto put = [&](int t, R val) {   // real output element t
+        if (STAGE_OUT) sreal(t) = val;
+        else if (valid) out_r[(long long)t * os_axis] = val;
+    };
+    auto store = [&](int k, Cx<R> y) {
+        if (PAIR_EPI) {
+            c.smem[c.addr(k)] = y;   // natural order; combined below
+        } else if (KIND == RK_C2R) {
+            if (!COLS && os_axis == 1) {
+                if (valid) reinterpret_cast<Cx<R>*>(out_r)[k] = cmake<R>(sc * y.x, -sc * y.y);
+            } else {
+                put(2 * k, sc * y.x);
+                put(2 * k + 1, -sc * y.y);
+            }
+        } else if (KIND == RK_DCT3) {
+            // v[2k] = y.x, v[2k+1] = -y.y;  x[o(t)] = v[t]/2, o(t) = 2t (t < N) else 2(n-1-t)+1
+            const int t0 = 2 * k, t1 = 2 * k + 1;
+            const R h = (R)0.5 * sc;
+            put(t0 < N ? 2 * t0 : 2 * (n - 1 - t0) + 1, h * y.x);
+            put(t1 < N ? 2 * t1 : 2 * (n - 1 - t1) + 1, -h * y.y);
+        } else {  // RK_DCT4
+            const Cx<R> C = cmul(y, ldg(&tabB[k]));
+            put(2 * k, sc * C.x);
+            put(n - 1 - 2 * k, -sc * C.y);
+        }
+    };
+
+    Cx<R> v[S::E];
+    SfftAll<R, S, L, COLS, 0, STAGE_IN, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
+
+    if (PAIR_EPI) {
+        __syncthreads();
+        // bins 0..N of the length-2N real DFT from the packed N-point result
+        for (int k = c.i; k <= N; k += S::TL) {
+            const Cx<R> zk = c.smem[c.addr(k == N ? 0 : k)];
+            const Cx<R> zc = cconj(c.smem[c.addr(k == 0 ? 0 : N - k)]);
+            const Cx<R> w = ldg(&tabA[k]);
+            const Cx<R> s = cadd(zk, zc), d = cmul(w, csub(zk, zc));
+            const Cx<R> X = cmake<R>((R)0.5 * (s.x + d.y), (R)0.5 * (s.y - d.x));
+            if (!valid) continue;
+            if (KIND == RK_R2C) {
+                out_c[(long long)k * os_axis] = cmake<R>(sc * X.x, sc * X.y);
+            } else if (KIND == RK_DCT1) {
+                out_r[(long long)k * os_axis] = (R)0.5 * sc * X.x;
+            } else {  // RK_DCT2
+                const Cx<R> A = cmul(X, ldg(&tabB[k]));
+                out_r[(long long)k * os_axis] = sc * A.x;
+                if (k > 0 && k < N) out_r[(long long)(n - k) * os_axis] = -sc * A.y;
+            }
+        }
+    }
+    if (STAGE_OUT) {
+        __syncthreads();
+        if (valid)
+            for (int t = c.i; t < n; t += S::TL) out_r[(long long)t * os_axis] = sreal(t);
+    }
 }
 
 }  // namespace ndfb

@@ -205,3 +205,48 @@ def test_four_step_through_fast_path(hs):
         hs.run("ndfft", 4096, (4096, 3), 0, np.float64, seed=7)
     finally:
         del os.environ["NDFB_FORCE_FOUR_STEP"]
+
+
+# ---- real-transform fast path (rsfft_kernel): R2C / C2R / DCT-I..IV around the Stockham core ----
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("op", ["ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4"])
+def test_rsfft_registered_lengths(hs, op, n, capfd):
+    import os
+    nn = n + 1 if op == "nddct1" else n      # DCT-I of n = 2^k + 1 points runs a 2^k-point core (benches/ndrustfft.rs:7)
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run(op, nn, (3, nn), 1, np.float64, seed=n)
+        hs.run(op, nn, (nn, 5), 0, np.float32, seed=n + 1)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    # core length n/2 = 32 has a column schedule only; everything longer runs both layouts on the fast path
+    core = n if op == "nddct1" else n // 2
+    want = (1 if 64 <= core <= 4096 else 0) + (1 if 32 <= core <= 4096 else 0)   # registered row / column schedules
+    assert err.count("[ndfb] rsfft") == want, err
+
+
+def test_rsfft_unaligned_rows_fall_back(hs, capfd):
+    """R2C rows read (x[2j], x[2j+1]) as one vector: an odd element offset must take the general kernel instead."""
+    import os
+    be = hs.be
+    rng = np.random.default_rng(3)
+    base = rng.uniform(-1, 1, (4, 129))
+    x = base[:, 1:]                         # rows start on an odd element
+    y = np.zeros((4, 65), complex); yo = np.zeros((4, 65), complex)
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        be.ndfft_r2c(x, y, be.R2cFftHandler(128), 1)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    orc.ndfft_r2c(np.ascontiguousarray(x), yo, orc.R2cFftHandler(128), 1)
+    assert orc.rel_l2(y, yo) < 1e-12
+    assert "[ndfb] rsfft" not in capfd.readouterr().err
+
+
+def test_rsfft_tail_tiles_and_3d(hs):
+    hs.run("nddct2", 128, (37, 128), 1, seed=1)
+    hs.run("nddct3", 128, (128, 37), 0, seed=2)
+    hs.run("ndfft_r2c", 256, (3, 256, 5), 1, seed=3)
+    hs.run("ndifft_r2c", 256, (2, 3, 256), 2, np.float32, seed=4, norm="none")
+    hs.run("nddct4", 64, (64, 3, 7), 0, np.float32, seed=5)
