@@ -102,6 +102,7 @@ struct TileArgs {
     double scale;          // multiplied into every output element
     // four-step (TK_C2C only): multiply output element k of lane j2 by W_fsN^{k*j2}
     int fs_twiddle;
+    int fs_dim;            // batch dim whose index is j2
     int fs_shift;          // W = hi[e >> fs_shift] * lo[e & ((1<<fs_shift)-1)], e = k*j2
     const void* fs_lo;
     const void* fs_hi;

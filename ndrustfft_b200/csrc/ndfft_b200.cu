@@ -175,6 +175,7 @@ struct LaunchSpec {
     int conj_in = 0, conj_out = 0;
     double scale = 1.0;
     int fs_twiddle = 0;
+    int fs_dim = 0;   // which batch dim carries the four-step index j2
     ndfb_plan::FsTw fs;
     bool keep_dim_order = false;
 };
@@ -267,7 +268,7 @@ static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::
 
     a.tw = c->d.tw; a.tabA = c->d.tabA; a.tabB = c->d.tabB; a.perm = c->d.perm;
     a.blu_c = c->d.blu_c; a.blu_bhat = c->d.blu_bhat;
-    a.fs_twiddle = s.fs_twiddle;
+    a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim;
     a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
 
     size_t smem = (((size_t)a.L * per_lane_over + 15) & ~(size_t)15) + (size_t)a.L * lane_bytes;
@@ -329,7 +330,7 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
         if (rc) return rc;
         a.tw = twd;
     }
-    a.fs_twiddle = s.fs_twiddle; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
+    a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
     const long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
     return e->launch(a, (unsigned)grid, stream);
@@ -468,20 +469,28 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     const long long cap1 = (long long)((cap - 256) / (4 * cs));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
     const long long cap2 = (long long)((cap - 256) / cs);
     if (!is_smooth(N)) return fail(NDFB_E_UNSUPPORTED, "length %lld has a prime factor > 13 and is too long for the single-pass Bluestein kernel", N);
-    // N1 * N2 = N, N1 <= cap1, N2 <= cap2, as square as possible
+    // N1 * N2 = N with both factors on chip; prefer factors that have an instantiated Stockham schedule (and, for the
+    // column pass, a tile at least one 32-byte sector wide), then the most square split
+    normalize_dims(dims);
+    const bool strided_lanes = !dims.empty() && llabs_(dims[0].is) < llabs_(is_axis) && llabs_(dims[0].os) < llabs_(os_axis);
     long long best1 = 0;
+    int best_score = -1;
     for (long long d = 1; d * d <= N; ++d) {
         if (N % d) continue;
         long long cands[2] = {d, N / d};
         for (long long n1 : cands) {
             long long n2 = N / n1;
             if (n1 > cap1 || n2 > cap2 || n1 < 2 || n2 < 2) continue;
-            if (best1 == 0 || llabs_(n1 - n2) < llabs_(best1 - N / best1)) best1 = n1;
+            int score = 0;
+            const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
+            const SfftEntry* e2 = find_sfft(sizeof(R) == 8, (int)n2, strided_lanes, 1 << 20);
+            if (e1 && (size_t)e1->L * cs >= 32) score += 2;
+            if (e2 && (!strided_lanes || (size_t)e2->L * cs >= 32)) score += 2;
+            if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
     }
     if (!best1) return fail(NDFB_E_UNSUPPORTED, "length %lld is too long for the two-pass decomposition (max about %lld)", N, cap1 * cap2);
     const long long N1 = best1, N2 = N / N1;
-    normalize_dims(dims);
     if ((int)dims.size() + 1 > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "four-step transform with more than %d batch dims", kMaxBatchDims - 1);
     long long nb = 1;
     for (auto& d : dims) nb *= d.size;
@@ -494,23 +503,45 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     if ((rc = ensure_device<R>(p, c2))) return rc;
     ndfb_plan::FsTw fs;
     if ((rc = get_fs_twiddles<R>(p, N, &fs))) return rc;
-    // pass 1: lanes (j2, batch...), transform over j1 (stride N2), twiddle W_N^{k1 j2}; ws[b][k1][j2]
-    LaunchSpec s1;
+    const bool strided = strided_lanes;
+    LaunchSpec s1, s2;
     s1.core = c1; s1.in = in; s1.out = ws;
-    s1.dims.push_back({N2, is_axis, 1});
-    long long wstride = N;
-    for (auto& d : dims) { s1.dims.push_back({d.size, d.is, wstride}); wstride *= d.size; }
-    s1.is_axis = N2 * is_axis; s1.os_axis = N2;
+    s2.core = c2; s2.in = ws; s2.out = out;
+    if (!strided) {
+        // pass 1: lanes (j2, batch...), transform over j1 (stride N2), twiddle W_N^{k1 j2}; ws[b][k1][j2]
+        s1.dims.push_back({N2, is_axis, 1});
+        long long wstride = N;
+        for (auto& d : dims) { s1.dims.push_back({d.size, d.is, wstride}); wstride *= d.size; }
+        s1.is_axis = N2 * is_axis; s1.os_axis = N2;
+        s1.fs_dim = 0;
+        // pass 2: lanes (k1, batch...), transform over j2 (contiguous), out[k1 + N1*k2]
+        s2.dims.push_back({N1, N2, os_axis});
+        wstride = N;
+        for (auto& d : dims) { s2.dims.push_back({d.size, wstride, d.os}); wstride *= d.size; }
+        s2.is_axis = 1; s2.os_axis = N1 * os_axis;
+    } else {
+        // strided columns: keep the fastest batch dim (adjacent columns) innermost in the workspace too,
+        // ws[outer][j][col], so that both passes read and write full rows of adjacent lanes
+        const long long W0 = dims[0].size;
+        s1.dims.push_back({W0, dims[0].is, 1});
+        s1.dims.push_back({N2, is_axis, W0});
+        long long wstride = N * W0;
+        for (size_t d = 1; d < dims.size(); ++d) { s1.dims.push_back({dims[d].size, dims[d].is, wstride}); wstride *= dims[d].size; }
+        s1.is_axis = N2 * is_axis; s1.os_axis = N2 * W0;
+        s1.fs_dim = 1;
+        s2.dims.push_back({W0, 1, dims[0].os});
+        s2.dims.push_back({N1, N2 * W0, os_axis});
+        wstride = N * W0;
+        for (size_t d = 1; d < dims.size(); ++d) { s2.dims.push_back({dims[d].size, wstride, dims[d].os}); wstride *= dims[d].size; }
+        s2.is_axis = W0; s2.os_axis = N1 * os_axis;
+    }
     s1.conj_in = inverse; s1.fs_twiddle = 1; s1.fs = fs;
     if ((rc = launch_c2c<R>(p, s1, stream))) return rc;
-    // pass 2: lanes (k1, batch...), transform over j2 (contiguous), out[k1 + N1*k2]
-    LaunchSpec s2;
-    s2.core = c2; s2.in = ws; s2.out = out;
-    s2.dims.push_back({N1, N2, os_axis});
-    wstride = N;
-    for (auto& d : dims) { s2.dims.push_back({d.size, wstride, d.os}); wstride *= d.size; }
-    s2.is_axis = 1; s2.os_axis = N1 * os_axis;
     s2.conj_out = inverse; s2.scale = scale;
+    {
+        const bool trace = std::getenv("NDFB_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[ndfb] four-step N=%lld = %lld x %lld (%s lanes)\n", N, N1, N2, strided ? "strided" : "contiguous");
+    }
     return launch_c2c<R>(p, s2, stream);
 }
 
@@ -593,6 +624,22 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         bool composite = false;
         for (size_t d = 2; d * d <= p->n; ++d) if (p->n % d == 0) composite = true;
         if (composite && is_smooth((long long)p->n)) single = false;
+    }
+    // long strided columns whose single-pass tile would be narrower than one 32-byte sector per row: two passes over
+    // full-width rows beat one pass over half sectors (c2 axis 0: 8192-point c64 columns)
+    if (single && o.tk == TK_C2C && is_smooth((long long)p->n) && p->n >= 1024) {
+        std::vector<BDim> nd = dims;
+        normalize_dims(nd);
+        long long nl = 1;
+        for (auto& d : nd) nl *= d.size;
+        const bool strided = !nd.empty() && nl > 1 && llabs_(nd[0].is) < llabs_(is_axis) && llabs_(nd[0].os) < llabs_(os_axis);
+        if (strided) {
+            const SfftEntry* e = find_sfft(sizeof(R) == 8, (int)p->n, true, nl);
+            const char* ov = std::getenv("NDFB_STRIDED_FOURSTEP");
+            bool narrow = e ? (size_t)e->L * cs < 32 : true;
+            if (ov) narrow = ov[0] == '1';
+            if (narrow) single = false;
+        }
     }
     if (single) {
         c = get_core(p, o.tk, (int)p->n);

@@ -27,7 +27,7 @@ struct SfftArgs {
     int conj_in, conj_out;
     double scale;
     const void* tw;  // per-pass twiddle tables in Sched::twoff layout
-    int fs_twiddle, fs_shift;
+    int fs_twiddle, fs_dim, fs_shift;
     const void* fs_lo;
     const void* fs_hi;
 };
@@ -138,7 +138,7 @@ struct LaneBase {
     int j2;
 };
 template <typename A>
-NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid) {
+NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0) {
     LaneBase o;
     o.bi = 0; o.bo = 0; o.j2 = 0;
     if (valid) {
@@ -147,7 +147,7 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid) {
             if (d < a.nbd) {
                 const long long q = g / a.bsz[d];
                 const long long rr = g - q * a.bsz[d];
-                if (d == 0) o.j2 = (int)rr;
+                if (d == fs_dim) o.j2 = (int)rr;
                 o.bi += rr * a.bis[d];
                 o.bo += rr * a.bos[d];
                 g = q;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     else { c.i = tid % S::TL; c.l = tid / S::TL; }
     const long long g = (long long)blockIdx.x * L + c.l;
     c.valid = g < a.nlanes;
-    const LaneBase lb = lane_base(a, g, c.valid);
+    const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
     const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
     Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
     const long long is_axis = a.is_axis, os_axis = a.os_axis;

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(512) tile_kernel(const __grid_constant__ TileA
             for (int d = 0; d < a.nbd; ++d) {
                 long long q = g / a.bsz[d];
                 long long r = g - q * a.bsz[d];
-                if (d == 0) j2 = (int)r;
+                if (d == a.fs_dim) j2 = (int)r;
                 bi += r * a.bis[d];
                 bo += r * a.bos[d];
                 g = q;

@@ -250,3 +250,20 @@ def test_rsfft_tail_tiles_and_3d(hs):
     hs.run("ndfft_r2c", 256, (3, 256, 5), 1, seed=3)
     hs.run("ndifft_r2c", 256, (2, 3, 256), 2, np.float32, seed=4, norm="none")
     hs.run("nddct4", 64, (64, 3, 7), 0, np.float32, seed=5)
+
+
+def test_strided_four_step(hs, capfd):
+    """Long strided columns whose one-pass tile would be narrower than a 32-byte sector take the two-pass route with the
+    adjacent columns kept innermost in the workspace (c2 axis 0 in BASELINE.json)."""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    os.environ["NDFB_STRIDED_FOURSTEP"] = "1"
+    try:
+        hs.run("ndfft", 1024, (1024, 20), 0, np.float32, seed=1)
+        hs.run("ndifft", 2048, (2048, 7), 0, np.float64, seed=2)
+        hs.run("ndfft", 1024, (3, 1024, 5), 1, np.float32, seed=3)
+    finally:
+        del os.environ["NDFB_TRACE"]
+        del os.environ["NDFB_STRIDED_FOURSTEP"]
+    err = capfd.readouterr().err
+    assert err.count("(strided lanes)") == 3, err
