@@ -115,10 +115,11 @@ static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
     int shift = 0;
     while ((1LL << (2 * shift)) < Ntot) ++shift;  // lo table ~ sqrt(N)
     if (shift < 1) shift = 1;
-    const long long nlo = 1LL << shift, nhi = ((Ntot - 1) >> shift) + 1;
+    if (Ntot <= (1LL << 17)) shift = 40;          // short enough for ONE table W_N^e, e = k1*j2 < N: no hi/lo product
+    const long long nlo = shift >= 40 ? Ntot : (1LL << shift), nhi = shift >= 40 ? 1 : ((Ntot - 1) >> shift) + 1;
     std::vector<cld> lo(nlo), hi(nhi);
     for (long long a = 0; a < nlo; ++a) lo[a] = unit_root(a, Ntot);
-    for (long long b = 0; b < nhi; ++b) hi[b] = unit_root(b << shift, Ntot);
+    for (long long b = 0; b < nhi; ++b) hi[b] = unit_root(shift >= 40 ? 0 : (b << shift), Ntot);
     ndfb_plan::FsTw t;
     t.shift = shift;
     int rc;

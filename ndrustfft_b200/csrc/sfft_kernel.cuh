@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
             const Cx<R>* lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
             const Cx<R>* hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
             const unsigned long long ee = (unsigned long long)k * (unsigned long long)j2;
-            y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
+            if (a.fs_shift >= 40) y = cmul(y, ldg(&lo[(unsigned)ee]));
+            else y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
         }
         out[(long long)k * os_axis] = y;
     };

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(512) tile_kernel(const __grid_constant__ TileA
                     const Cx<R>* lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
                     const Cx<R>* hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
                     unsigned long long e = (unsigned long long)k * (unsigned long long)c.lane_j2[l];
-                    Cx<R> w = cmul(ldg(&hi[e >> a.fs_shift]), ldg(&lo[e & ((1ull << a.fs_shift) - 1)]));
+                    Cx<R> w = a.fs_shift >= 40 ? ldg(&lo[e]) : cmul(ldg(&hi[e >> a.fs_shift]), ldg(&lo[e & ((1ull << a.fs_shift) - 1)]));
                     y = cmul(y, w);
                 }
                 out_c[g] = y;

@@ -1,0 +1,113 @@
+"""Multi-GPU drivers for the axis-transform hot path (one process per GPU, torch.distributed for the plumbing).
+
+Two forms exist:
+
+* single-axis calls shard over lanes with NO collective: `shard_bounds` / `sharded_apply` split a non-transformed
+  axis across ranks and every rank calls the ordinary nd* function on its slice (lanes are independent,
+  reference src/lib.rs:120-124);
+* a full 3-D real transform (BASELINE config c3: `ndfft_r2c` on the last axis, then `ndfft` on axes 1 and 0, the
+  pattern of examples/rfft2.rs:29-33) needs exactly one exchange: `SlabR2cFft3d` keeps axis-0 slabs for the first
+  two passes, re-partitions to axis-1 slabs with one all-to-all over NCCL/NVLink and runs the last pass locally.
+
+The result of `SlabR2cFft3d.forward` is left distributed along axis 1 (documented; `inverse` takes it from there).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import FftHandler, R2cFftHandler, _default_backend
+
+
+def shard_bounds(n, world, rank):
+    """[lo, hi) of `rank`'s share when `n` items are split as evenly as possible over `world` ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sharded_apply(fn, inp, out, handler, axis, shard_axis, world, rank):
+    """Run `fn(inp_slice, out_slice, handler, axis)` on this rank's slice along `shard_axis` (!= axis).  No communication."""
+    if shard_axis == axis:
+        raise ValueError("cannot shard along the transformed axis")
+    lo, hi = shard_bounds(inp.shape[shard_axis], world, rank)
+    sl = [slice(None)] * inp.ndim
+    sl[shard_axis] = slice(lo, hi)
+    if hi > lo:
+        fn(inp[tuple(sl)], out[tuple(sl)], handler, axis)
+    return lo, hi
+
+
+class SlabR2cFft3d:
+    """Slab-decomposed 3-D real-to-complex FFT of a global (n0, n1, n2) array over `world` ranks.
+
+    Rank r owns x[r*n0/P:(r+1)*n0/P, :, :] on input and X[:, r*n1/P:(r+1)*n1/P, :] (m = n2//2+1 last) on output.
+    n0 and n1 must be divisible by the world size (512 is, for P = 2, 4, 8; the 257-long axis is never split)."""
+
+    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n0, self.n1, self.n2 = (int(v) for v in shape)
+        self.m = self.n2 // 2 + 1
+        P = self.world
+        if self.n0 % P or self.n1 % P:
+            raise ValueError(f"n0={self.n0} and n1={self.n1} must be divisible by the world size {P}")
+        self.s0, self.s1 = self.n0 // P, self.n1 // P
+        self.rdt = np.dtype(dtype)
+        self.device = device if device is not None else torch.device("cpu")
+        self.be = backend or _default_backend()
+        dev_index = self.device.index if getattr(self.device, "type", "cpu") == "cuda" else 0
+        self.h2 = self.be.R2cFftHandler(self.n2, self.rdt, dev_index or 0)
+        self.h1 = self.be.FftHandler(self.n1, self.rdt, dev_index or 0)
+        self.h0 = self.be.FftHandler(self.n0, self.rdt, dev_index or 0)
+        self.ct = torch.complex64 if self.rdt == np.float32 else torch.complex128
+        self.rt = torch.float32 if self.rdt == np.float32 else torch.float64
+        # work buffers (kept across calls)
+        self.a = torch.empty((self.s0, self.n1, self.m), dtype=self.ct, device=self.device)
+        self.b = torch.empty((self.s0, self.n1, self.m), dtype=self.ct, device=self.device)
+        self.send = torch.empty((P, self.s0, self.s1, self.m), dtype=self.ct, device=self.device)
+        self.recv = torch.empty((P, self.s0, self.s1, self.m), dtype=self.ct, device=self.device)
+
+    # bytes each rank sends over the wire per all-to-all (for NVLink-roofline reporting)
+    def bytes_sent_per_rank(self):
+        P = self.world
+        return (P - 1) * self.s0 * self.s1 * self.m * (8 if self.rdt == np.float32 else 16)
+
+    def _all_to_all(self, recv, send):
+        if self.world == 1:
+            recv.copy_(send)
+            return
+        t = self.torch
+        self.dist.all_to_all_single(t.view_as_real(recv), t.view_as_real(send), group=self.group)
+
+    def forward(self, x, out=None):
+        """x: (n0/P, n1, n2) real -> (n0, n1/P, m) complex."""
+        t, be, P = self.torch, self.be, self.world
+        assert tuple(x.shape) == (self.s0, self.n1, self.n2), x.shape
+        be.ndfft_r2c(x, self.a, self.h2, 2)
+        be.ndfft(self.a, self.b, self.h1, 1)
+        # pack: chunk p = my rows, columns p*s1:(p+1)*s1  (one strided device copy)
+        self.send.copy_(self.b.view(self.s0, P, self.s1, self.m).permute(1, 0, 2, 3))
+        self._all_to_all(self.recv, self.send)
+        slab = self.recv.view(self.n0, self.s1, self.m)     # chunk q holds rows q*s0:(q+1)*s0 -> already (n0, s1, m)
+        if out is None:
+            out = t.empty((self.n0, self.s1, self.m), dtype=self.ct, device=self.device)
+        be.ndfft(slab, out, self.h0, 0)
+        return out
+
+    def inverse(self, X, out=None):
+        """X: (n0, n1/P, m) complex -> (n0/P, n1, n2) real (Normalization::Default: exact inverse of `forward`)."""
+        t, be, P = self.torch, self.be, self.world
+        assert tuple(X.shape) == (self.n0, self.s1, self.m), X.shape
+        slab = self.recv.view(self.n0, self.s1, self.m)
+        be.ndifft(X, slab, self.h0, 0)
+        self._all_to_all(self.send, self.recv)               # chunk p of `send` now holds columns p*s1.. of my rows
+        self.b.view(self.s0, P, self.s1, self.m).copy_(self.send.permute(1, 0, 2, 3))
+        be.ndifft(self.b, self.a, self.h1, 1)
+        if out is None:
+            out = t.empty((self.s0, self.n1, self.n2), dtype=self.rt, device=self.device)
+        be.ndifft_r2c(self.a, out, self.h2, 2)
+        return out
