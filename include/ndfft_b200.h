@@ -98,6 +98,18 @@ NDFB_API int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double ex
                      const size_t* shape_out, const ptrdiff_t* strides_out,
                      int axis, int mem, void* stream);
 
+/* ndfft / ndifft on DEVICE memory whose OUTPUT axis is stored in blocks: output element k of a lane goes to
+ *   lane_base + (k / out_block) * out_block_stride + (k % out_block) * strides_out[axis]
+ * (elements).  This is the packed send layout of a slab all-to-all: the axis pass writes each destination rank's
+ * chunk contiguously (or straight into a peer-mapped buffer), so the transpose needs no separate pack kernel.
+ * No counterpart in the reference (it has no distributed path); used by ndrustfft_b200.dist. */
+NDFB_API int ndfb_exec_split_out(const ndfb_plan* plan, int op, int norm, double extra_scale,
+                        size_t out_block, ptrdiff_t out_block_stride,
+                        const void* in, void* out, int ndim,
+                        const size_t* shape_in, const ptrdiff_t* strides_in,
+                        const size_t* shape_out, const ptrdiff_t* strides_out,
+                        int axis, void* stream);
+
 /* Thread-local message of the last failing call on this thread ("" if none). */
 NDFB_API const char* ndfb_last_error(void);
 

@@ -192,6 +192,23 @@ class Backend:
             ctypes.c_void_p(vi.stream or 0))
         self.lib.check(rc)
 
+    def ndfft_split_out(self, input, output, handler, axis, out_shape, out_strides, out_block, out_block_stride, inverse=False):
+        """ndfft / ndifft on device tensors with the output axis stored in blocks (ndfb_exec_split_out): element k of an
+        output lane lands at `(k // out_block) * out_block_stride + (k % out_block) * out_strides[axis]` from the lane base.
+        `output` only provides the base pointer; `out_shape` / `out_strides` describe the logical output array."""
+        vi, vo = _view_of(input), _view_of(output)
+        if (vi.device is None or vo.device is None) and "emu" not in self.lib.version():
+            raise ValueError("split-output transforms take device tensors")
+        ndim = len(vi.shape)
+        SZ = ctypes.c_size_t * ndim
+        PD = ctypes.c_ssize_t * ndim
+        norm = _lib.NORM_DEFAULT if handler.norm.kind == "default" else _lib.NORM_NONE
+        rc = self.lib.dll.ndfb_exec_split_out(
+            handler._plan, _lib.OP_IFFT if inverse else _lib.OP_FFT, norm, 1.0, int(out_block), int(out_block_stride),
+            ctypes.c_void_p(vi.ptr), ctypes.c_void_p(vo.ptr), ndim, SZ(*vi.shape), PD(*vi.strides),
+            SZ(*out_shape), PD(*out_strides), int(axis), ctypes.c_void_p(vi.stream or 0))
+        self.lib.check(rc)
+
     # -- Custom normalisation plumbing (host callback; SURVEY.md 7.2-7) --
     @staticmethod
     def _to_host(a):

@@ -106,6 +106,9 @@ struct TileArgs {
     int fs_shift;          // W = hi[e >> fs_shift] * lo[e & ((1<<fs_shift)-1)], e = k*j2
     const void* fs_lo;
     const void* fs_hi;
+    // TK_C2C only: output axis index k split as (k / os_blk, k % os_blk) with stride os_blk_stride for the block index
+    int os_blk;
+    long long os_blk_stride;
 };
 
 }  // namespace ndfb

@@ -177,6 +177,8 @@ struct LaunchSpec {
     double scale = 1.0;
     int fs_twiddle = 0;
     int fs_dim = 0;   // which batch dim carries the four-step index j2
+    int os_blk = 0;   // split output axis (see TileArgs::os_blk)
+    long long os_blk_stride = 0;
     ndfb_plan::FsTw fs;
     bool keep_dim_order = false;
 };
@@ -271,6 +273,7 @@ static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::
     a.blu_c = c->d.blu_c; a.blu_bhat = c->d.blu_bhat;
     a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim;
     a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
+    a.os_blk = s.os_blk; a.os_blk_stride = s.os_blk_stride;
 
     size_t smem = (((size_t)a.L * per_lane_over + 15) & ~(size_t)15) + (size_t)a.L * lane_bytes;
     const long long grid = (nlanes + a.L - 1) / a.L;
@@ -332,6 +335,7 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
         a.tw = twd;
     }
     a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
+    a.os_blk = s.os_blk; a.os_blk_stride = s.os_blk_stride;
     const long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
     return e->launch(a, (unsigned)grid, stream);
@@ -553,6 +557,8 @@ struct OpInfo {
     int conj_in = 0, conj_out = 0;
     double scale = 1.0;
     const char* what = "fft";
+    int os_blk = 0;
+    long long os_blk_stride = 0;
 };
 
 static int op_info(const ndfb_plan* p, int op, int norm, OpInfo* o) {
@@ -621,14 +627,14 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         if ((size_t)N_est * cs + 64 > cap) single = false;
     }
     // test hook: exercise the two-pass path at sizes the emulator/tests can afford
-    if (single && o.tk == TK_C2C && p->n >= 4 && std::getenv("NDFB_FORCE_FOUR_STEP")) {
+    if (single && o.tk == TK_C2C && !o.os_blk && p->n >= 4 && std::getenv("NDFB_FORCE_FOUR_STEP")) {
         bool composite = false;
         for (size_t d = 2; d * d <= p->n; ++d) if (p->n % d == 0) composite = true;
         if (composite && is_smooth((long long)p->n)) single = false;
     }
     // long strided columns whose single-pass tile would be narrower than one 32-byte sector per row: two passes over
     // full-width rows beat one pass over half sectors (c2 axis 0: 8192-point c64 columns)
-    if (single && o.tk == TK_C2C && is_smooth((long long)p->n) && p->n >= 1024) {
+    if (single && o.tk == TK_C2C && !o.os_blk && is_smooth((long long)p->n) && p->n >= 1024) {
         std::vector<BDim> nd = dims;
         normalize_dims(nd);
         long long nl = 1;
@@ -646,6 +652,7 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         c = get_core(p, o.tk, (int)p->n);
         if (!fits_one_tile(p, c->t, cs)) single = false;
     }
+    if (!single && o.os_blk) return fail(NDFB_E_UNSUPPORTED, "split output axis is only available for single-pass complex transforms");
     if (!single) {
         if (o.tk != TK_C2C)
             return fail(NDFB_E_UNSUPPORTED, "%s of length %zu does not fit one CTA's shared memory; only complex-to-complex has a multi-pass path in this build", o.what, p->n);
@@ -667,6 +674,7 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
             s.core = c; s.in = (const char*)in + io * (long long)ie; s.out = (char*)out + oo * (long long)oe;
             s.dims = inner; s.is_axis = is_axis; s.os_axis = os_axis;
             s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
+            s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride;
             if ((rc = (o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream)))) return rc;
         }
         return 0;
@@ -674,6 +682,7 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
     LaunchSpec s;
     s.core = c; s.in = in; s.out = out; s.dims = dims; s.is_axis = is_axis; s.os_axis = os_axis;
     s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
+    s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride;
     return o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream);
 }
 
@@ -769,9 +778,19 @@ static int check_call(const ndfb_plan* p, const OpInfo& o, int ndim, const size_
     return 0;
 }
 
+static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, ptrdiff_t out_block_stride,
+                       const void* in, void* out, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
+                       const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream);
+
 int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale, const void* in, void* out, int ndim,
                      const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
                      const ptrdiff_t* strides_out, int axis, int mem, void* stream) {
+    return exec_common(plan, op, norm, extra_scale, 0, 0, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+}
+
+static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, ptrdiff_t out_block_stride,
+                       const void* in, void* out, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
+                       const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream) {
     if (!plan || !shape_in || !strides_in || !shape_out || !strides_out) return fail(NDFB_E_INVALID, "null argument");
     if (ndim < 1 || ndim > NDFB_MAX_DIMS) return fail(NDFB_E_INVALID, "ndim %d outside 1..%d", ndim, NDFB_MAX_DIMS);
     if (norm != NDFB_NORM_NONE && norm != NDFB_NORM_DEFAULT) return fail(NDFB_E_INVALID, "unknown norm %d", norm);
@@ -781,6 +800,7 @@ int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale
     int rc = op_info(p, op, norm, &o);
     if (rc) return rc;
     if ((rc = check_call(p, o, ndim, shape_in, shape_out, axis))) return rc;
+    o.os_blk = (int)out_block; o.os_blk_stride = (long long)out_block_stride;
     bool empty = false;
     for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) empty = true;
     if (empty) return NDFB_OK;
@@ -788,6 +808,16 @@ int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale
     if (p->dtype == NDFB_F32)
         return exec_any<float>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
     return exec_any<double>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+}
+
+int ndfb_exec_split_out(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, ptrdiff_t out_block_stride,
+                        const void* in, void* out, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
+                        const size_t* shape_out, const ptrdiff_t* strides_out, int axis, void* stream) {
+    if (op != NDFB_OP_FFT && op != NDFB_OP_IFFT) return fail(NDFB_E_UNSUPPORTED, "split output axis is only available for ndfft / ndifft");
+    if (out_block == 0 || (axis >= 0 && axis < ndim && shape_out && shape_out[axis] % out_block))
+        return fail(NDFB_E_INVALID, "out_block must divide the output lane length");
+    return exec_common(plan, op, norm, extra_scale, out_block, out_block_stride, in, out, ndim, shape_in, strides_in, shape_out, strides_out,
+                       axis, NDFB_MEM_DEVICE, stream);
 }
 
 int ndfb_exec(const ndfb_plan* plan, int op, int norm, const void* in, void* out, int ndim, const size_t* shape_in,

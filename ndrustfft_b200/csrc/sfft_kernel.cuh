@@ -28,6 +28,8 @@ struct SfftArgs {
     double scale;
     const void* tw;  // per-pass twiddle tables in Sched::twoff layout
     int fs_twiddle, fs_dim, fs_shift;
+    int os_blk;            // != 0: output axis index k is split as (k / os_blk, k % os_blk) ...
+    long long os_blk_stride;  // ... with this stride for the block index (packed all-to-all send layout)
     const void* fs_lo;
     const void* fs_hi;
 };
@@ -196,7 +198,8 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
             if (a.fs_shift >= 40) y = cmul(y, ldg(&lo[(unsigned)ee]));
             else y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
         }
-        out[(long long)k * os_axis] = y;
+        if (a.os_blk) out[(long long)(k / a.os_blk) * a.os_blk_stride + (long long)(k % a.os_blk) * os_axis] = y;
+        else out[(long long)k * os_axis] = y;
     };
     SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
 }

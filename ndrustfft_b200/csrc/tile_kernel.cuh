@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(512) tile_kernel(const __grid_constant__ TileA
                     Cx<R> w = a.fs_shift >= 40 ? ldg(&lo[e]) : cmul(ldg(&hi[e >> a.fs_shift]), ldg(&lo[e & ((1ull << a.fs_shift) - 1)]));
                     y = cmul(y, w);
                 }
-                out_c[g] = y;
+                if (a.os_blk) out_c[c.lb_out[l] + (long long)(k / a.os_blk) * a.os_blk_stride + (long long)(k % a.os_blk) * a.os_axis] = y;
+                else out_c[g] = y;
             } break;
             case TK_R2C_EVEN: out_c[g] = cscale(post(l, k), scale); break;
             case TK_R2C_ODD: out_c[g] = cscale(Y(l, k), scale); break;

@@ -41,9 +41,16 @@ class SlabR2cFft3d:
     """Slab-decomposed 3-D real-to-complex FFT of a global (n0, n1, n2) array over `world` ranks.
 
     Rank r owns x[r*n0/P:(r+1)*n0/P, :, :] on input and X[:, r*n1/P:(r+1)*n1/P, :] (m = n2//2+1 last) on output.
-    n0 and n1 must be divisible by the world size (512 is, for P = 2, 4, 8; the 257-long axis is never split)."""
+    n0 and n1 must be divisible by the world size (512 is, for P = 2, 4, 8; the 257-long axis is never split).
 
-    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None):
+    Pipeline (forward), `chunks` pieces of the spectrum axis i2 in flight:
+        r2c along axis 2 (whole slab)
+        for each i2-chunk c:   ndfft along axis 1, its store writing the PACKED all-to-all layout [dest][i0][j1][i2c]
+                               directly (ndfb_exec_split_out: no separate pack kernel), then an async all-to-all of c
+        for each i2-chunk c:   wait for c, ndfft along axis 0 into out[:, :, c]      (overlaps the exchange of c+1..)
+    """
+
+    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=4):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -65,49 +72,70 @@ class SlabR2cFft3d:
         self.h0 = self.be.FftHandler(self.n0, self.rdt, dev_index or 0)
         self.ct = torch.complex64 if self.rdt == np.float32 else torch.complex128
         self.rt = torch.float32 if self.rdt == np.float32 else torch.float64
-        # work buffers (kept across calls)
         self.a = torch.empty((self.s0, self.n1, self.m), dtype=self.ct, device=self.device)
         self.b = torch.empty((self.s0, self.n1, self.m), dtype=self.ct, device=self.device)
-        self.send = torch.empty((P, self.s0, self.s1, self.m), dtype=self.ct, device=self.device)
-        self.recv = torch.empty((P, self.s0, self.s1, self.m), dtype=self.ct, device=self.device)
+        # i2 chunks and their send / receive buffers
+        k = max(1, min(int(chunks), self.m)) if P > 1 else 1
+        self.chunks = [shard_bounds(self.m, k, c) for c in range(k)]
+        if P > 1:
+            self.send = [torch.empty(P * self.s0 * self.s1 * (hi - lo), dtype=self.ct, device=self.device) for lo, hi in self.chunks]
+            self.recv = [torch.empty(P * self.s0 * self.s1 * (hi - lo), dtype=self.ct, device=self.device) for lo, hi in self.chunks]
 
     # bytes each rank sends over the wire per all-to-all (for NVLink-roofline reporting)
     def bytes_sent_per_rank(self):
         P = self.world
         return (P - 1) * self.s0 * self.s1 * self.m * (8 if self.rdt == np.float32 else 16)
 
-    def _all_to_all(self, recv, send):
-        if self.world == 1:
-            recv.copy_(send)
-            return
+    def _a2a(self, recv, send):
         t = self.torch
-        self.dist.all_to_all_single(t.view_as_real(recv), t.view_as_real(send), group=self.group)
+        return self.dist.all_to_all_single(t.view_as_real(recv), t.view_as_real(send), group=self.group, async_op=True)
 
     def forward(self, x, out=None):
         """x: (n0/P, n1, n2) real -> (n0, n1/P, m) complex."""
         t, be, P = self.torch, self.be, self.world
-        assert tuple(x.shape) == (self.s0, self.n1, self.n2), x.shape
-        be.ndfft_r2c(x, self.a, self.h2, 2)
-        be.ndfft(self.a, self.b, self.h1, 1)
-        # pack: chunk p = my rows, columns p*s1:(p+1)*s1  (one strided device copy)
-        self.send.copy_(self.b.view(self.s0, P, self.s1, self.m).permute(1, 0, 2, 3))
-        self._all_to_all(self.recv, self.send)
-        slab = self.recv.view(self.n0, self.s1, self.m)     # chunk q holds rows q*s0:(q+1)*s0 -> already (n0, s1, m)
+        s0, s1, n0, n1 = self.s0, self.s1, self.n0, self.n1
+        assert tuple(x.shape) == (s0, n1, self.n2), x.shape
         if out is None:
-            out = t.empty((self.n0, self.s1, self.m), dtype=self.ct, device=self.device)
-        be.ndfft(slab, out, self.h0, 0)
+            out = t.empty((n0, s1, self.m), dtype=self.ct, device=self.device)
+        be.ndfft_r2c(x, self.a, self.h2, 2)
+        if P == 1:
+            be.ndfft(self.a, self.b, self.h1, 1)
+            be.ndfft(self.b, out, self.h0, 0)
+            return out
+        works = []
+        for c, (lo, hi) in enumerate(self.chunks):
+            mc = hi - lo
+            # element (i0, i1 = p*s1 + j1, i2) -> send[c][p][i0][j1][i2 - lo]
+            be.ndfft_split_out(self.a[:, :, lo:hi], self.send[c], self.h1, 1,
+                               out_shape=(s0, n1, mc), out_strides=(s1 * mc, mc, 1),
+                               out_block=s1, out_block_stride=s0 * s1 * mc)
+            works.append(self._a2a(self.recv[c], self.send[c]))
+        for c, (lo, hi) in enumerate(self.chunks):
+            works[c].wait()
+            # chunk q of recv holds rows q*s0:(q+1)*s0 -> already the (n0, s1, mc) axis-1 slab
+            be.ndfft(self.recv[c].view(n0, s1, hi - lo), out[:, :, lo:hi], self.h0, 0)
         return out
 
     def inverse(self, X, out=None):
         """X: (n0, n1/P, m) complex -> (n0/P, n1, n2) real (Normalization::Default: exact inverse of `forward`)."""
         t, be, P = self.torch, self.be, self.world
-        assert tuple(X.shape) == (self.n0, self.s1, self.m), X.shape
-        slab = self.recv.view(self.n0, self.s1, self.m)
-        be.ndifft(X, slab, self.h0, 0)
-        self._all_to_all(self.send, self.recv)               # chunk p of `send` now holds columns p*s1.. of my rows
-        self.b.view(self.s0, P, self.s1, self.m).copy_(self.send.permute(1, 0, 2, 3))
-        be.ndifft(self.b, self.a, self.h1, 1)
+        s0, s1, n0, n1 = self.s0, self.s1, self.n0, self.n1
+        assert tuple(X.shape) == (n0, s1, self.m), X.shape
         if out is None:
-            out = t.empty((self.s0, self.n1, self.n2), dtype=self.rt, device=self.device)
+            out = t.empty((s0, n1, self.n2), dtype=self.rt, device=self.device)
+        if P == 1:
+            be.ndifft(X, self.b, self.h0, 0)
+            be.ndifft(self.b, self.a, self.h1, 1)
+            be.ndifft_r2c(self.a, out, self.h2, 2)
+            return out
+        works = []
+        for c, (lo, hi) in enumerate(self.chunks):
+            be.ndifft(X[:, :, lo:hi], self.recv[c].view(n0, s1, hi - lo), self.h0, 0)
+            works.append(self._a2a(self.send[c], self.recv[c]))     # send[c][p] = columns p*s1.. of my rows
+        for c, (lo, hi) in enumerate(self.chunks):
+            mc = hi - lo
+            works[c].wait()
+            self.b[:, :, lo:hi].copy_(self.send[c].view(P, s0, s1, mc).permute(1, 0, 2, 3).reshape(s0, n1, mc))
+        be.ndifft(self.b, self.a, self.h1, 1)
         be.ndifft_r2c(self.a, out, self.h2, 2)
         return out

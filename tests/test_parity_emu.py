@@ -268,3 +268,26 @@ def test_strided_four_step(hs, capfd):
         del os.environ["NDFB_STRIDED_FOURSTEP"]
     err = capfd.readouterr().err
     assert err.count("(strided lanes)") == 3, err
+
+
+def test_split_output_axis(hs):
+    """ndfb_exec_split_out: the packed all-to-all send layout written directly by the axis pass."""
+    be = hs.be
+    rng = np.random.default_rng(9)
+    s0, n1, mc, P = 3, 12, 5, 4
+    s1 = n1 // P
+    x = rng.uniform(-1, 1, (s0, n1, mc)) + 1j * rng.uniform(-1, 1, (s0, n1, mc))
+    send = np.zeros(P * s0 * s1 * mc, complex)
+    be.ndfft_split_out(x, send, be.FftHandler(n1), 1, out_shape=(s0, n1, mc), out_strides=(s1 * mc, mc, 1),
+                       out_block=s1, out_block_stride=s0 * s1 * mc)
+    want = np.fft.fft(x, axis=1).reshape(s0, P, s1, mc).transpose(1, 0, 2, 3).ravel()
+    assert orc.rel_l2(send, want) < 1e-12
+    # 64-point lanes take the Stockham fast path; same layout contract
+    n1, P = 64, 2
+    s1 = n1 // P
+    x = rng.uniform(-1, 1, (s0, n1, mc)) + 1j * rng.uniform(-1, 1, (s0, n1, mc))
+    send = np.zeros(P * s0 * s1 * mc, complex)
+    be.ndfft_split_out(x, send, be.FftHandler(n1), 1, out_shape=(s0, n1, mc), out_strides=(s1 * mc, mc, 1),
+                       out_block=s1, out_block_stride=s0 * s1 * mc, inverse=True)
+    want = np.fft.ifft(x, axis=1).reshape(s0, P, s1, mc).transpose(1, 0, 2, 3).ravel()
+    assert orc.rel_l2(send, want) < 1e-12
