@@ -184,23 +184,50 @@ struct LaunchSpec {
 };
 
 // ---- fast path lookup ----
+// Which schedule family to prefer: 'A' (few passes, many registers) or 'B' (more CTAs per SM).  The default table
+// below comes from same-run A/B measurements on B200 (tools/tune_variants.py, profiles/r1f_tune*.jsonl);
+// NDFB_SFFT_FAMILY=A|B overrides it for measurements.
+static int preferred_family(bool f64, int N, bool cols, bool real_kind) {
+    if (const char* f = std::getenv("NDFB_SFFT_FAMILY")) return (f[0] == 'B' || f[0] == 'b') ? 1 : 0;
+    (void)N; (void)cols; (void)real_kind;
+    return f64 ? 1 : 0;
+}
+
+template <typename E>
+static bool better_entry(const E* e, const E* best, long long nlanes, int pref_fam) {
+    if (!best) return true;
+    // 1. a tile not much wider than the batch, 2. the preferred family, 3. a tile that lets two CTAs share an SM,
+    // 4. the widest tile
+    const bool e_fit = e->L <= 2 * nlanes, b_fit = best->L <= 2 * nlanes;
+    if (e_fit != b_fit) return e_fit;
+    const bool e_f = e->fam == pref_fam, b_f = best->fam == pref_fam;
+    if (e_f != b_f) return e_f;
+    const bool e_ok = e->smem <= 112 * 1024, b_ok = best->smem <= 112 * 1024;
+    if (e_ok != b_ok) return e_ok;
+    return e->L > best->L;
+}
+
 static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes) {
     static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
     if (disabled) return nullptr;
     const SfftEntry* tabs[4] = {kSfft_f32_rows, kSfft_f32_cols, kSfft_f64_rows, kSfft_f64_cols};
     const int counts[4] = {kSfft_f32_rows_count, kSfft_f32_cols_count, kSfft_f64_rows_count, kSfft_f64_cols_count};
     const int which = (f64 ? 2 : 0) + (cols ? 1 : 0);
+    // measurement hook: NDFB_SFFT_PICK=<N>:<index> takes the index-th registry entry of that length
+    if (const char* pick = std::getenv("NDFB_SFFT_PICK")) {
+        int pn = 0, pi = 0;
+        if (sscanf(pick, "%d:%d", &pn, &pi) == 2 && pn == N) {
+            int seen = 0;
+            for (int i = 0; i < counts[which]; ++i)
+                if (tabs[which][i].N == N && seen++ == pi) return &tabs[which][i];
+        }
+    }
+    const int pref = preferred_family(f64, N, cols, false);
     const SfftEntry* best = nullptr;
     for (int i = 0; i < counts[which]; ++i) {
         const SfftEntry* e = &tabs[which][i];
         if (e->N != N) continue;
-        if (!best) { best = e; continue; }
-        // prefer the widest tile that still lets two CTAs share an SM; never a tile much wider than the batch
-        const bool e_ok = e->smem <= 112 * 1024, b_ok = best->smem <= 112 * 1024;
-        const bool e_fit = e->L <= 2 * nlanes, b_fit = best->L <= 2 * nlanes;
-        if (e_fit != b_fit) { if (e_fit) best = e; continue; }
-        if (e_ok != b_ok) { if (e_ok) best = e; continue; }
-        if (e->L > best->L) best = e;
+        if (better_entry(e, best, nlanes, pref)) best = e;
     }
     return best;
 }
@@ -371,12 +398,13 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
 #include "rsfft_tables.inc"
     };
 #undef RSFFT_TABLE
+    const int pref = preferred_family(f64, N, cols, true);
     const RsfftEntry* best = nullptr;
     for (const Tab& t : tabs)
         for (int i = 0; i < t.n; ++i) {
             const RsfftEntry* e = &t.e[i];
             if (e->f64 != (f64 ? 1 : 0) || e->kind != rkind || e->N != N || e->cols != (cols ? 1 : 0)) continue;
-            if (!best || (e->L <= 2 * nlanes && e->L > best->L)) best = e;
+            if (better_entry(e, best, nlanes, pref)) best = e;
         }
     return best;
 }

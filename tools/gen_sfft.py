@@ -1,10 +1,17 @@
 #!/usr/bin/env python3
-"""Generates the instantiation lists of the fast Stockham kernel (ndrustfft_b200/csrc/sfft_inst_*.cu).
+"""Generates the instantiation lists of the fast Stockham kernels (ndrustfft_b200/csrc/{sfft,rsfft}_inst_*.cu).
 
 Run `python tools/gen_sfft.py` after changing the schedule rules; the generated files are committed.
-One entry = (dtype, N, threads-per-lane TL, radices, lanes per CTA L, rows|cols layout, min CTAs/SM).
+One entry = (dtype, N, threads-per-lane TL, radices, lanes per CTA L, rows|cols layout, min CTAs/SM, family).
+
+Two schedule families are instantiated and the host picks per case (csrc/ndfft_b200.cu: find_sfft / find_rsfft):
+  family A: few passes, many registers  (radix 16, f32 last pass radix 32; E = 16/32 points per thread)
+  family B: more CTAs per SM            (radix 8 for f64, 16 for f32;      E = 8/16 points per thread)
+Measured on B200 (profiles/r1f_tune*.jsonl): B wins wherever occupancy is the limiter (e.g. 512-point f64 rows
+81 % vs 64 % of the HBM roofline).
 """
 import os
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "ndrustfft_b200", "csrc")
@@ -18,169 +25,176 @@ MIXED = {  # N: (TL, radices)   ({2,3,5}-smooth lengths of BASELINE config c5a a
     60: (10, [6, 10]),
     216: (36, [6, 6, 6]),
     600: (100, [6, 10, 10]),
-    3600: (600, [6, 6, 10, 10]),
 }
 
 
-def pow2_schedule(N, f64):
-    emax = 16 if f64 else 32
+def pow2_schedule(N, f64, fam):
+    if fam == 0:
+        emax, rbase = (16 if f64 else 32), 16
+    else:
+        emax, rbase = (8 if f64 else 16), (8 if f64 else 16)
     if N <= emax:
         return 1, [N]
-    rad = []
-    rem = N
+    rad, rem = [], N
     while rem > 1:
-        r = min(16, rem)
+        r = min(rbase, rem)
         rad.append(r)
         rem //= r
-    # f32: merge a trailing small radix into a radix-32 last pass (fewer exchanges)
-    if not f64 and len(rad) >= 2 and rad[-1] == 2 and rad[-2] == 16:
-        rad = rad[:-2] + [32]
-    E = max(rad)
-    return N // E, rad
+    if fam == 0 and not f64 and len(rad) >= 2 and rad[-1] == 2 and rad[-2] == 16:
+        rad = rad[:-2] + [32]            # f32: one radix-32 last pass instead of 16 then 2
+    if len(rad) > 4:
+        return None
+    return N // max(rad), rad
 
 
-def schedule(N, f64):
+def schedule(N, f64, fam):
     if N in MIXED:
-        return MIXED[N]
-    return pow2_schedule(N, f64)
+        return MIXED[N] if fam == 0 else None
+    return pow2_schedule(N, f64, fam)
 
 
 def npad(N, r0):
     return N + N // r0
 
 
-def entry(f64, N, L, cols):
-    TL, rad = schedule(N, f64)
-    rad4 = rad + [1] * (4 - len(rad))
+def make(f64, N, TL, rad, L, cols, fam, minb=None, always_smem=False):
     cs = 16 if f64 else 8
     T = TL * L
-    smem = L * npad(N, rad[0]) * cs if len(rad) > 1 else 0
+    smem = L * npad(N, rad[0]) * cs if (len(rad) > 1 or always_smem) else 0
     E = max(-(-(N // r) // TL) * r for r in rad)
-    regs = E * (4 if f64 else 2) + (56 if f64 else 44)
-    regs = min(regs, 255)
-    minb = max(1, min(65536 // (T * regs), (227 * 1024) // max(smem, 1) if smem else 8, 8))
-    return dict(f64=f64, N=N, TL=TL, rad=rad4, L=L, cols=cols, minb=minb, T=T, smem=smem, E=E)
+    if minb is None:
+        regs = E * (4 if f64 else 2) + (32 if fam == 1 else (56 if f64 else 44))
+        regs = min(regs, 255)
+        minb = max(1, min(65536 // (T * regs), (227 * 1024) // max(smem, 1) if smem else 8, 8))
+    return dict(f64=f64, N=N, TL=TL, rad=rad + [1] * (4 - len(rad)), L=L, cols=cols, minb=minb, T=T, smem=smem, E=E, fam=fam)
 
 
-def rows_entries(f64):
+def rows_L(N, TL, r0, cs):
+    L = max(1, 256 // TL)
+    while L > 1 and L * npad(N, r0) * cs > 72 * 1024:
+        L //= 2
+    p = 1
+    while p * 2 <= L:
+        p *= 2
+    return p
+
+
+def c2c_rows(f64):
     out = []
     cs = 16 if f64 else 8
-    sizes = [64, 128, 256, 512, 1024, 2048, 4096, 8192] + ([] if f64 else [16384]) + sorted(MIXED)
-    for N in sizes:
-        TL, rad = schedule(N, f64)
-        if TL > 512:
+    for fam in (0, 1):
+        for N in [64, 128, 256, 512, 1024, 2048, 4096, 8192] + sorted(MIXED):
+            sc = schedule(N, f64, fam)
+            if sc is None:
+                continue
+            TL, rad = sc
+            if TL > 512 or TL < 2:
+                continue
+            e = make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam)
+            if e["smem"] <= 220 * 1024 and 32 <= e["T"] <= 1024:
+                out.append(e)
+    return dedup(out)
+
+
+def c2c_cols(f64):
+    out = []
+    cs = 16 if f64 else 8
+    for fam in (0, 1):
+        for N in [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192] + sorted(MIXED):
+            sc = schedule(N, f64, fam)
+            if sc is None:
+                continue
+            TL, rad = sc
+            cand = []
+            for L in (32, 16, 8, 4, 2):
+                if L * cs > (256 if N <= 256 else 128):   # short columns: 256-byte rows keep enough loads in flight per CTA
+                    continue
+                e = make(f64, N, TL, rad, L, 1, fam)
+                if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
+                    continue
+                cand.append(e)
+            out.extend(cand[:2])  # the two widest tiles that fit
+    return dedup(out)
+
+
+def real_entries(f64):
+    out = []
+    rs = 8 if f64 else 4
+    cs = 2 * rs
+    for fam in (0, 1):
+        for N in [64, 128, 256, 512, 1024, 2048, 4096]:
+            sc = schedule(N, f64, fam)
+            if sc is None:
+                continue
+            TL, rad = sc
+            if TL < 2 or TL > 512:
+                continue
+            out.append(make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam, always_smem=True))
+        for N in [32, 64, 128, 256, 512, 1024, 2048, 4096]:
+            sc = schedule(N, f64, fam)
+            if sc is None:
+                continue
+            TL, rad = sc
+            for L in (32, 16, 8, 4, 2):
+                if L * rs > 128:
+                    continue
+                e = make(f64, N, TL, rad, L, 1, fam, always_smem=True)
+                if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
+                    continue
+                out.append(e)
+                break
+    return dedup(out)
+
+
+def dedup(entries):
+    seen, out = set(), []
+    for e in entries:
+        key = (e["f64"], e["N"], e["TL"], tuple(e["rad"]), e["L"], e["cols"], e["minb"])
+        if key in seen:
             continue
-        L = max(1, 256 // TL)
-        while L > 1 and L * npad(N, rad[0]) * cs > 72 * 1024:
-            L //= 2
-        p = 1
-        while p * 2 <= L:
-            p *= 2
-        e = entry(f64, N, p, 0)
-        if e["smem"] <= 220 * 1024 and 32 <= e["T"] <= 1024:
-            out.append(e)
-    return out
-
-
-def cols_entries(f64):
-    out = []
-    cs = 16 if f64 else 8
-    sizes = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192] + sorted(MIXED)
-    for N in sizes:
-        cand = []
-        for L in (32, 16, 8, 4, 2):
-            if L * cs > (256 if N <= 256 else 128):   # short columns: 256-byte rows keep enough loads in flight per CTA
-                continue
-            e = entry(f64, N, L, 1)
-            if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
-                continue
-            cand.append(e)
-        out.extend(cand[:2])  # the two widest tiles that fit
-    return out
-
-
-RKINDS = ["RK_R2C", "RK_C2R", "RK_DCT1", "RK_DCT2", "RK_DCT3", "RK_DCT4"]
-
-
-def r_rows_entries(f64):
-    out = []
-    cs = 16 if f64 else 8
-    for N in [64, 128, 256, 512, 1024, 2048, 4096]:
-        TL, rad = schedule(N, f64)
-        L = max(1, 256 // TL)
-        while L > 1 and L * npad(N, rad[0]) * cs > 72 * 1024:
-            L //= 2
-        e = entry(f64, N, L, 0)
-        e["smem"] = L * npad(N, rad[0]) * cs
+        seen.add(key)
         out.append(e)
     return out
 
 
-def r_cols_entries(f64):
-    out = []
-    rs = 8 if f64 else 4
-    cs = 2 * rs
-    for N in [32, 64, 128, 256, 512, 1024, 2048, 4096]:
-        cand = []
-        for L in (32, 16, 8, 4, 2):
-            if L * rs > 128:
-                continue
-            e = entry(f64, N, L, 1)
-            e["smem"] = L * npad(N, schedule(N, f64)[1][0]) * cs
-            if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
-                continue
-            cand.append(e)
-        out.extend(cand[:1])
-    return out
+def fmt(e, macro, extra=""):
+    R = "double" if e["f64"] else "float"
+    r = e["rad"]
+    return (f"    {macro}({R}, {e['f64']}, {extra}{e['N']}, {e['TL']}, {r[0]}, {r[1]}, {r[2]}, {r[3]}, {e['L']}, {e['cols']}, {e['minb']}, {e['fam']}),"
+            f"  // T={e['T']} smem={e['smem']} E={e['E']}")
 
 
-def emit_r(name, kind, entries):
-    lines = ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "sfft_inst.h"', "", "namespace ndfb {", "",
-             f"const RsfftEntry kRsfft_{name}[] = {{"]
-    for e in entries:
-        R = "double" if e["f64"] else "float"
-        r = e["rad"]
-        lines.append(f"    RSFFT_ENTRY({R}, {e['f64']}, {kind}, {e['N']}, {e['TL']}, {r[0]}, {r[1]}, {r[2]}, {r[3]}, {e['L']}, {e['cols']}, {e['minb']}),"
-                     f"  // T={e['T']} smem={e['smem']} E={e['E']}")
-    lines += ["};", f"const int kRsfft_{name}_count = {len(entries)};", "", "}  // namespace ndfb", ""]
-    with open(os.path.join(OUT, f"rsfft_inst_{name}.cu"), "w") as f:
-        f.write("\n".join(lines))
-    return len(entries)
-
-
-def emit(name, entries):
-    lines = ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "sfft_inst.h"', "", "namespace ndfb {", "",
-             f"const SfftEntry kSfft_{name}[] = {{"]
-    for e in entries:
-        R = "double" if e["f64"] else "float"
-        r = e["rad"]
-        lines.append(f"    SFFT_ENTRY({R}, {e['f64']}, {e['N']}, {e['TL']}, {r[0]}, {r[1]}, {r[2]}, {r[3]}, {e['L']}, {e['cols']}, {e['minb']}),"
-                     f"  // T={e['T']} smem={e['smem']} E={e['E']}")
-    lines += ["};", f"const int kSfft_{name}_count = {len(entries)};", "", "}  // namespace ndfb", ""]
-    with open(os.path.join(OUT, f"sfft_inst_{name}.cu"), "w") as f:
-        f.write("\n".join(lines))
-    return len(entries)
+def write(path, lines):
+    with open(os.path.join(OUT, path), "w") as f:
+        f.write("\n".join(lines) + "\n")
 
 
 def main():
+    for f in os.listdir(OUT):
+        if f.startswith(("sfft_inst_", "rsfft_inst_")) and f.endswith(".cu"):
+            os.remove(os.path.join(OUT, f))
     total = 0
-    groups = {"f32_rows": rows_entries(0), "f32_cols": cols_entries(0), "f64_rows": rows_entries(1), "f64_cols": cols_entries(1)}
+    head = ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "sfft_inst.h"', "", "namespace ndfb {", ""]
+    groups = {"f32_rows": c2c_rows(0), "f32_cols": c2c_cols(0), "f64_rows": c2c_rows(1), "f64_cols": c2c_cols(1)}
     for name, ents in groups.items():
-        total += emit(name, ents)
+        write(f"sfft_inst_{name}.cu", head + [f"const SfftEntry kSfft_{name}[] = {{"] + [fmt(e, "SFFT_ENTRY") for e in ents] +
+              ["};", f"const int kSfft_{name}_count = {len(ents)};", "", "}  // namespace ndfb"])
+        total += len(ents)
     rnames = []
     for f64 in (0, 1):
-        for kind in RKINDS:
+        ents = real_entries(f64)
+        for kind in ["RK_R2C", "RK_C2R", "RK_DCT1", "RK_DCT2", "RK_DCT3", "RK_DCT4"]:
             nm = f"{'f64' if f64 else 'f32'}_{kind[3:].lower()}"
-            total += emit_r(nm, kind, r_rows_entries(f64) + r_cols_entries(f64))
+            write(f"rsfft_inst_{nm}.cu", head + [f"const RsfftEntry kRsfft_{nm}[] = {{"] + [fmt(e, "RSFFT_ENTRY", kind + ", ") for e in ents] +
+                  ["};", f"const int kRsfft_{nm}_count = {len(ents)};", "", "}  // namespace ndfb"])
+            total += len(ents)
             rnames.append(nm)
-    with open(os.path.join(OUT, "rsfft_tables.inc"), "w") as f:
-        f.write("// GENERATED by tools/gen_sfft.py — do not edit.\n")
-        for nm in rnames:
-            f.write(f"RSFFT_TABLE({nm})\n")
+    write("rsfft_tables.inc", ["// GENERATED by tools/gen_sfft.py — do not edit."] + [f"RSFFT_TABLE({nm})" for nm in rnames])
     print("generated", total, "instances")
-    for name, ents in groups.items():
-        for e in ents:
-            print(name, e["N"], e["rad"], "TL", e["TL"], "L", e["L"], "T", e["T"], "smem", e["smem"], "E", e["E"], "minb", e["minb"])
+    if "-v" in sys.argv:
+        for name, ents in groups.items():
+            for e in ents:
+                print(name, e)
 
 
 if __name__ == "__main__":
