@@ -250,4 +250,46 @@ struct DftTwiceOdd {
 template <typename R> struct Dft<R, 6> : DftTwiceOdd<R, 3> {};
 template <typename R> struct Dft<R, 10> : DftTwiceOdd<R, 5> {};
 
+// ---- composite radix N = A x B by one Cooley-Tukey step with constant twiddles (used for 9 = 3 x 3) ----
+template <int N> NDFB_HD constexpr double ct_cos(int m);
+template <int N> NDFB_HD constexpr double ct_sin(int m);
+template <> NDFB_HD constexpr double ct_cos<9>(int m) {
+    constexpr double t[9] = {1.0, 0.7660444431189780352023927, 0.1736481776669303488517166, -0.5, -0.9396926207859083840541093, -0.9396926207859083840541093, -0.5, 0.1736481776669303488517166, 0.7660444431189780352023927};
+    return t[m];
+}
+template <> NDFB_HD constexpr double ct_sin<9>(int m) {
+    constexpr double t[9] = {0.0, 0.6427876096865393263226434, 0.984807753012208059366743, 0.8660254037844386467637232, 0.3420201433256687330440996, -0.3420201433256687330440996, -0.8660254037844386467637232, -0.984807753012208059366743, -0.6427876096865393263226434};
+    return t[m];
+}
+
+template <typename R, int A, int B>
+struct DftCT {
+    static NDFB_DEV void run(Cx<R>* v) {
+        constexpr int N = A * B;
+        Cx<R> a[A][B];
+#pragma unroll
+        for (int j0 = 0; j0 < A; ++j0) {
+            Cx<R> u[B];
+#pragma unroll
+            for (int j1 = 0; j1 < B; ++j1) u[j1] = v[j0 + A * j1];
+            Dft<R, B>::run(u);
+#pragma unroll
+            for (int k0 = 0; k0 < B; ++k0) {
+                if (j0 * k0 == 0) a[j0][k0] = u[k0];
+                else a[j0][k0] = cmul(u[k0], cmake<R>((R)ct_cos<N>((j0 * k0) % N), (R)-ct_sin<N>((j0 * k0) % N)));
+            }
+        }
+#pragma unroll
+        for (int k0 = 0; k0 < B; ++k0) {
+            Cx<R> w[A];
+#pragma unroll
+            for (int j0 = 0; j0 < A; ++j0) w[j0] = a[j0][k0];
+            Dft<R, A>::run(w);
+#pragma unroll
+            for (int k1 = 0; k1 < A; ++k1) v[k0 + B * k1] = w[k1];
+        }
+    }
+};
+template <typename R> struct Dft<R, 9> : DftCT<R, 3, 3> {};
+
 }  // namespace ndfb

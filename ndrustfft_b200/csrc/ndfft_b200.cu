@@ -189,13 +189,20 @@ struct LaunchSpec {
 // NDFB_SFFT_FAMILY=A|B overrides it for measurements.
 static int preferred_family(bool f64, int N, bool cols, bool real_kind) {
     if (const char* f = std::getenv("NDFB_SFFT_FAMILY")) return (f[0] == 'B' || f[0] == 'b') ? 1 : 0;
-    (void)N; (void)cols; (void)real_kind;
-    return f64 ? 1 : 0;
+    // B won every same-run comparison except where its tile is narrower than a 32-byte sector per row (handled by
+    // better_entry's first rule): c3 0.46 ms vs 0.52-0.56 ms, c2 rows 0.308 vs 0.329 ms, c4 rows 0.11-0.125 vs 0.126-0.145 ms.
+    (void)f64; (void)N; (void)cols; (void)real_kind;
+    return 1;
 }
 
 template <typename E>
-static bool better_entry(const E* e, const E* best, long long nlanes, int pref_fam) {
+static bool better_entry(const E* e, const E* best, long long nlanes, int pref_fam, size_t lane_elem_bytes) {
     if (!best) return true;
+    // 0. strided tiles must cover at least one 32-byte sector per row
+    if (e->cols) {
+        const bool e_sec = (size_t)e->L * lane_elem_bytes >= 32, b_sec = (size_t)best->L * lane_elem_bytes >= 32;
+        if (e_sec != b_sec) return e_sec;
+    }
     // 1. a tile not much wider than the batch, 2. the preferred family, 3. a tile that lets two CTAs share an SM,
     // 4. the widest tile
     const bool e_fit = e->L <= 2 * nlanes, b_fit = best->L <= 2 * nlanes;
@@ -227,7 +234,7 @@ static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes) 
     for (int i = 0; i < counts[which]; ++i) {
         const SfftEntry* e = &tabs[which][i];
         if (e->N != N) continue;
-        if (better_entry(e, best, nlanes, pref)) best = e;
+        if (better_entry(e, best, nlanes, pref, f64 ? (size_t)16 : (size_t)8)) best = e;
     }
     return best;
 }
@@ -404,7 +411,7 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
         for (int i = 0; i < t.n; ++i) {
             const RsfftEntry* e = &t.e[i];
             if (e->f64 != (f64 ? 1 : 0) || e->kind != rkind || e->N != N || e->cols != (cols ? 1 : 0)) continue;
-            if (better_entry(e, best, nlanes, pref)) best = e;
+            if (better_entry(e, best, nlanes, pref, f64 ? (size_t)8 : (size_t)4)) best = e;
         }
     return best;
 }

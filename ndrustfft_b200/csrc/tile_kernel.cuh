@@ -119,6 +119,7 @@ NDFB_DEV void radix_dispatch(const TileCtx<R>& c, int radix, int B, int ns, bool
         case 5: radix_pass<R, 5, DIT>(c, B, ns, lane_fast); break;
         case 7: radix_pass<R, 7, DIT>(c, B, ns, lane_fast); break;
         case 8: radix_pass<R, 8, DIT>(c, B, ns, lane_fast); break;
+        case 9: radix_pass<R, 9, DIT>(c, B, ns, lane_fast); break;
         case 11: radix_pass<R, 11, DIT>(c, B, ns, lane_fast); break;
         case 13: radix_pass<R, 13, DIT>(c, B, ns, lane_fast); break;
         case 16: radix_pass<R, 16, DIT>(c, B, ns, lane_fast); break;

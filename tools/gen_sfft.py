@@ -25,6 +25,9 @@ MIXED = {  # N: (TL, radices)   ({2,3,5}-smooth lengths of BASELINE config c5a a
     60: (10, [6, 10]),
     216: (36, [6, 6, 6]),
     600: (100, [6, 10, 10]),
+    81: (9, [9, 9]),
+    729: (81, [9, 9, 9]),
+    4095: (512, [13, 9, 7, 5]),   # DCT-I of 4096 points (BASELINE c4): core 4095 = 3^2 5 7 13
 }
 
 
@@ -122,7 +125,7 @@ def real_entries(f64):
     rs = 8 if f64 else 4
     cs = 2 * rs
     for fam in (0, 1):
-        for N in [64, 128, 256, 512, 1024, 2048, 4096]:
+        for N in [64, 128, 256, 512, 1024, 2048, 4096, 4095]:
             sc = schedule(N, f64, fam)
             if sc is None:
                 continue
