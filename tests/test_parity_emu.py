@@ -291,3 +291,17 @@ def test_split_output_axis(hs):
                        out_block=s1, out_block_stride=s0 * s1 * mc, inverse=True)
     want = np.fft.ifft(x, axis=1).reshape(s0, P, s1, mc).transpose(1, 0, 2, 3).ravel()
     assert orc.rel_l2(send, want) < 1e-12
+
+
+def test_dct1_4096_runs_the_4095_point_schedule(hs, capfd):
+    """BASELINE c4: nddct1 on 4096 points needs a 4095 = 13 * 9 * 7 * 5 point core (radix-13/9/7/5 Stockham passes)."""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run("nddct1", 4096, (2, 4096), 1, np.float64, seed=1)
+        hs.run("ndfft", 729, (729, 3), 0, np.float32, seed=2)       # 9 * 9 * 9
+        hs.run("ndifft", 81, (4, 81), 1, np.float64, seed=3)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    assert "rsfft kind=2 f64 N=4095" in err and err.count("[ndfb] sfft") == 2, err
