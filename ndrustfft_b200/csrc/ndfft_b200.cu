@@ -735,6 +735,77 @@ static void span_of(int ndim, const size_t* shape, const ptrdiff_t* strides, siz
     *dense = (mx - mn + 1) == count;
 }
 
+#ifndef NDFB_EMU
+struct HostPipe {
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    static constexpr int kMaxChunks = 16;
+    cudaEvent_t ev_in[kMaxChunks], ev_k[kMaxChunks];
+    int device = -1;
+    int init(int dev) {
+        if (device == dev) return 0;
+        for (int i = 0; i < 3; ++i) NDFB_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) {
+            NDFB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            NDFB_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+        }
+        device = dev;
+        return 0;
+    }
+};
+static thread_local HostPipe g_pipe;
+
+static bool is_c_order(int ndim, const size_t* shape, const ptrdiff_t* strides) {
+    long long expect = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        if (shape[d] != 1 && strides[d] != expect) return false;
+        expect *= (long long)shape[d];
+    }
+    return true;
+}
+
+template <typename R>
+static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, void* din, void* dout,
+                               int ndim, const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
+                               const ptrdiff_t* strides_out, int axis, size_t ie, size_t oe, int* done) {
+    *done = 0;
+    if (ndim < 2 || std::getenv("NDFB_NO_HOST_PIPELINE")) return 0;
+    if (!is_c_order(ndim, shape_in, strides_in) || !is_c_order(ndim, shape_out, strides_out)) return 0;
+    size_t total_in = ie, total_out = oe;
+    for (int d = 0; d < ndim; ++d) { total_in *= shape_in[d]; total_out *= shape_out[d]; }
+    if (total_in + total_out < (size_t)(16u << 20)) return 0;
+    const int d = axis == 0 ? 1 : 0;               // split dim: outermost non-transformed dim
+    const size_t nd = shape_in[d];
+    int K = 8;
+    while (K > 1 && (nd / K < 1 || (total_in / K) < (size_t)(2u << 20))) K /= 2;
+    if (K < 2 || nd < (size_t)K) return 0;
+    int rc = g_pipe.init(p->device);
+    if (rc) return rc;
+    // 2-D copy geometry of one chunk [lo, hi) of dim d:  d == 0: one contiguous range; d == 1 (axis 0): shape[0] rows
+    std::vector<size_t> shi(shape_in, shape_in + ndim), sho(shape_out, shape_out + ndim);
+    for (int c = 0; c < K; ++c) {
+        const size_t lo = nd * c / K, hi = nd * (c + 1) / K;
+        if (hi == lo) continue;
+        shi[d] = sho[d] = hi - lo;
+        const size_t ioff = lo * (size_t)strides_in[d] * ie, ooff = lo * (size_t)strides_out[d] * oe;
+        const size_t iw = (hi - lo) * (size_t)strides_in[d] * ie, ow = (hi - lo) * (size_t)strides_out[d] * oe;
+        const size_t irows = d == 0 ? 1 : shape_in[0], orows = d == 0 ? 1 : shape_out[0];
+        const size_t ipitch = d == 0 ? iw : (size_t)strides_in[0] * ie, opitch = d == 0 ? ow : (size_t)strides_out[0] * oe;
+        NDFB_CUDA(cudaMemcpy2DAsync((char*)din + ioff, ipitch, (const char*)in + ioff, ipitch, iw, irows, cudaMemcpyHostToDevice, g_pipe.s[0]));
+        NDFB_CUDA(cudaEventRecord(g_pipe.ev_in[c], g_pipe.s[0]));
+        NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ev_in[c], 0));
+        rc = exec_device<R>(p, o, extra_scale, (const char*)din + ioff, (char*)dout + ooff, ndim, shi.data(), strides_in, sho.data(),
+                            strides_out, axis, g_pipe.s[1]);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        NDFB_CUDA(cudaEventRecord(g_pipe.ev_k[c], g_pipe.s[1]));
+        NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[2], g_pipe.ev_k[c], 0));
+        NDFB_CUDA(cudaMemcpy2DAsync((char*)out + ooff, opitch, (const char*)dout + ooff, opitch, ow, orows, cudaMemcpyDeviceToHost, g_pipe.s[2]));
+    }
+    NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[2]));
+    *done = 1;
+    return 0;
+}
+#endif
+
 template <typename R>
 static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, int ndim,
                     const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
@@ -754,6 +825,16 @@ static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const voi
     void *din = nullptr, *dout = nullptr;
     if ((rc = g_pool.get(0, p->device, (size_t)(ihi - ilo), &din))) return rc;
     if ((rc = g_pool.get(1, p->device, (size_t)(ohi - olo), &dout))) return rc;
+#ifndef NDFB_EMU
+    // Large standard-layout arrays: split along a non-transformed dim and pipeline H2D(c+1) | kernel(c) | D2H(c-1)
+    // on three streams, so the two PCIe directions and the GPU work overlap (the array is 2 x 512 MiB for c2).
+    {
+        int done = 0;
+        rc = exec_host_pipelined<R>(p, o, extra_scale, in, out, din, dout, ndim, shape_in, strides_in, shape_out, strides_out,
+                                    axis, ie, oe, &done);
+        if (rc || done) return rc;
+    }
+#endif
     if ((rc = dev_h2d(din, (const char*)in + ilo, (size_t)(ihi - ilo), stream))) return rc;
     if (!odense) {  // keep the bytes between output elements intact
         if ((rc = dev_h2d(dout, (const char*)out + olo, (size_t)(ohi - olo), stream))) return rc;

@@ -57,6 +57,13 @@ struct Sched {
     // one pad element per R0 points keeps the stride-R0 writes of pass 0 off a single bank
     static constexpr int pad(int a) { return a + a / R0_; }
     static constexpr int NPAD = N_ + N_ / R0_;
+    // Address fast paths: when the per-thread part and the compile-time part of an index are each multiples of R0
+    // where it matters, pad(thread + const) = pad(thread) + pad(const) and every shared-memory access becomes
+    // "one precomputed register + immediate offset".
+    static constexpr bool fast_read(int p) { return p >= 1 && p < NP && TL_ % R0_ == 0 && nbf(p) % R0_ == 0; }
+    static constexpr bool fast_write(int p) {
+        return p == 0 ? true : (p < NP - 1 && TL_ % before(p) == 0 && before(p) % R0_ == 0);
+    }
 };
 
 template <typename R, class S, int L, bool COLS>
@@ -68,6 +75,9 @@ struct SfftCtx {
         const int p = S::pad(a);
         return COLS ? p * L + l : l * S::NPAD + p;
     }
+    // slot of padded position `pp` (already padded)
+    NDFB_DEV int slot_of(int pp) const { return COLS ? pp * L + l : l * S::NPAD + pp; }
+    static constexpr int kscale = COLS ? L : 1;   // slot distance of one padded position
 };
 
 // One Stockham pass.  Butterfly b of this pass (b < N/r) reads X[b + q N/r], multiplies by W_{P r}^{q k}
@@ -85,9 +95,15 @@ struct SfftPass {
     static constexpr bool LAST = PASS == S::NP - 1;
     static constexpr bool FULL = (NB % S::TL) == 0;  // no idle threads in this pass
 
+    static constexpr bool FR = S::fast_read(PASS);
+    static constexpr bool FW = !LAST && S::fast_write(PASS);
+    static constexpr bool KCONST = !FIRST && (S::TL % P == 0);   // k = b mod P does not depend on m
+
     template <typename LoadF, typename StoreF>
     static NDFB_DEV void run(const SfftCtx<R, S, L, COLS>& c, Cx<R> (&v)[S::E], const Cx<R>* __restrict__ tw,
                              LoadF load, StoreF store) {
+        // ---- gather this thread's butterfly inputs ----
+        const int rbase = FR ? c.slot_of(S::pad(c.i)) : 0;
 #pragma unroll
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
@@ -95,19 +111,24 @@ struct SfftPass {
 #pragma unroll
                 for (int q = 0; q < r; ++q) {
                     if (FIRST) v[m * r + q] = load(b + q * NB);
+                    else if (FR) v[m * r + q] = c.smem[rbase + S::pad(S::TL * m + q * NB) * c.kscale];
                     else v[m * r + q] = c.smem[c.addr(b + q * NB)];
                 }
             }
         }
         // every thread has read the previous layout before it is overwritten
         if ((!FIRST && !LAST) || (FIRST && SYNC0 && !LAST) || (LAST && SYNCL)) __syncthreads();
+        const int k0 = c.i % P;
+        const Cx<R>* __restrict__ twp0 = tw + S::twoff(PASS) + k0;
+        // write base for the fast paths:  pass 0: b (R0 + 1);  later passes: pad((i - k) r + k)
+        const int wbase = !FW ? 0 : (FIRST ? c.slot_of(c.i * (S::R0 + 1)) : c.slot_of(S::pad((c.i - k0) * r + k0)));
 #pragma unroll
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
             if (FULL || b < NB) {
-                const int k = b % P;
+                const int k = KCONST ? k0 : b % P;
                 if (!FIRST) {
-                    const Cx<R>* __restrict__ twp = tw + S::twoff(PASS) + k;
+                    const Cx<R>* __restrict__ twp = KCONST ? twp0 : tw + S::twoff(PASS) + k;
 #pragma unroll
                     for (int q = 1; q < r; ++q) v[m * r + q] = cmul(v[m * r + q], ldg(&twp[(q - 1) * P]));
                 }
@@ -115,6 +136,13 @@ struct SfftPass {
                 if (LAST) {
 #pragma unroll
                     for (int q = 0; q < r; ++q) store(b + q * NB, v[m * r + q]);   // (b-k) r + k + q P with P = N/r, k = b
+                } else if (FW) {
+#pragma unroll
+                    for (int q = 0; q < r; ++q) {
+                        // pass 0: pad(b r + q) = b (r + 1) + q;  later: pad(thread part) + pad(TL m r + q P)
+                        const int cpart = FIRST ? (S::TL * m * (S::R0 + 1) + q) : S::pad(S::TL * m * r + q * P);
+                        c.smem[wbase + cpart * c.kscale] = v[m * r + q];
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < r; ++q) c.smem[c.addr((b - k) * r + k + q * P)] = v[m * r + q];
@@ -144,15 +172,31 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0)
     LaneBase o;
     o.bi = 0; o.bo = 0; o.j2 = 0;
     if (valid) {
+        if (a.nlanes <= 0x7fffffffLL) {   // 32-bit index arithmetic (a 64-bit division costs ~80 instructions)
+            unsigned g32 = (unsigned)g;
 #pragma unroll
-        for (int d = 0; d < kMaxBatchDims; ++d) {
-            if (d < a.nbd) {
-                const long long q = g / a.bsz[d];
-                const long long rr = g - q * a.bsz[d];
-                if (d == fs_dim) o.j2 = (int)rr;
-                o.bi += rr * a.bis[d];
-                o.bo += rr * a.bos[d];
-                g = q;
+            for (int d = 0; d < kMaxBatchDims; ++d) {
+                if (d < a.nbd) {
+                    const unsigned sz = (unsigned)a.bsz[d];
+                    const unsigned q = g32 / sz;
+                    const unsigned rr = g32 - q * sz;
+                    if (d == fs_dim) o.j2 = (int)rr;
+                    o.bi += (long long)rr * a.bis[d];
+                    o.bo += (long long)rr * a.bos[d];
+                    g32 = q;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < kMaxBatchDims; ++d) {
+                if (d < a.nbd) {
+                    const long long q = g / a.bsz[d];
+                    const long long rr = g - q * a.bsz[d];
+                    if (d == fs_dim) o.j2 = (int)rr;
+                    o.bi += rr * a.bis[d];
+                    o.bo += rr * a.bos[d];
+                    g = q;
+                }
             }
         }
     }
@@ -162,6 +206,42 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0)
 // ------------------------------------------------------------------------------------------------------
 // complex-to-complex
 // ------------------------------------------------------------------------------------------------------
+// PLAIN: no four-step twiddle and no split output axis;  UNIT: both axis strides are 1 (contiguous rows)
+template <typename R, class S, int L, bool COLS, bool PLAIN, bool UNIT>
+NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, const LaneBase& lb) {
+    const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
+    Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
+    const long long is_axis = UNIT ? 1 : a.is_axis, os_axis = UNIT ? 1 : a.os_axis;
+    const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
+    const R sc = (R)a.scale;
+    const R sy = a.conj_out ? -sc : sc;
+    const R sgn_in = a.conj_in ? (R)-1 : (R)1;
+    const bool valid = c.valid;
+    const int j2 = lb.j2;
+    Cx<R> v[S::E];
+    auto load = [&](int j) -> Cx<R> {
+        Cx<R> x = valid ? in[(long long)j * is_axis] : cmake<R>((R)0, (R)0);
+        x.y *= sgn_in;
+        return x;
+    };
+    auto store = [&](int k, Cx<R> val) {
+        if (!valid) return;
+        Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
+        if (!PLAIN) {
+            if (a.fs_twiddle) {
+                const Cx<R>* lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
+                const Cx<R>* hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
+                const unsigned long long ee = (unsigned long long)k * (unsigned long long)j2;
+                if (a.fs_shift >= 40) y = cmul(y, ldg(&lo[(unsigned)ee]));
+                else y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
+            }
+            if (a.os_blk) { out[(long long)(k / a.os_blk) * a.os_blk_stride + (long long)(k % a.os_blk) * os_axis] = y; return; }
+        }
+        out[(long long)k * os_axis] = y;
+    };
+    SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
+}
+
 template <typename R, class S, int L, bool COLS, int MINB>
 __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_constant__ SfftArgs a) {
     NDFB_DYN_SMEM(smem_raw);
@@ -173,35 +253,10 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     const long long g = (long long)blockIdx.x * L + c.l;
     c.valid = g < a.nlanes;
     const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
-    const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
-    Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
-    const long long is_axis = a.is_axis, os_axis = a.os_axis;
-    const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
-    const R sc = (R)a.scale;
-    const R sy = a.conj_out ? -sc : sc;
-    const bool cj = a.conj_in != 0;
-    const bool valid = c.valid;
-    const int j2 = lb.j2;
-    Cx<R> v[S::E];
-    auto load = [&](int j) -> Cx<R> {
-        Cx<R> x = valid ? in[(long long)j * is_axis] : cmake<R>((R)0, (R)0);
-        if (cj) x.y = -x.y;
-        return x;
-    };
-    auto store = [&](int k, Cx<R> val) {
-        if (!valid) return;
-        Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
-        if (a.fs_twiddle) {
-            const Cx<R>* lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
-            const Cx<R>* hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
-            const unsigned long long ee = (unsigned long long)k * (unsigned long long)j2;
-            if (a.fs_shift >= 40) y = cmul(y, ldg(&lo[(unsigned)ee]));
-            else y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
-        }
-        if (a.os_blk) out[(long long)(k / a.os_blk) * a.os_blk_stride + (long long)(k % a.os_blk) * os_axis] = y;
-        else out[(long long)k * os_axis] = y;
-    };
-    SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
+    const bool plain = !a.fs_twiddle && !a.os_blk;
+    if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, true, true>(a, c, lb);
+    else if (plain) sfft_body<R, S, L, COLS, true, false>(a, c, lb);
+    else sfft_body<R, S, L, COLS, false, false>(a, c, lb);
 }
 
 // ------------------------------------------------------------------------------------------------------
