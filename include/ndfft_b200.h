@@ -110,6 +110,17 @@ NDFB_API int ndfb_exec_split_out(const ndfb_plan* plan, int op, int norm, double
                         const size_t* shape_out, const ptrdiff_t* strides_out,
                         int axis, void* stream);
 
+/* Same, but block p of every output lane is written relative to block_ptrs[p] (device pointers, 1..8 of them, e.g. the
+ * peer-mapped receive buffers of the other GPUs): element k lands at
+ *   block_ptrs[k / out_block] + lane_offset + (k % out_block) * strides_out[axis].
+ * With NVLink peer mappings the axis pass's store IS the all-to-all of the slab transpose (fused compute + collective). */
+NDFB_API int ndfb_exec_scatter_out(const ndfb_plan* plan, int op, int norm, double extra_scale,
+                          size_t out_block, int nblocks, void* const* block_ptrs,
+                          const void* in, int ndim,
+                          const size_t* shape_in, const ptrdiff_t* strides_in,
+                          const size_t* shape_out, const ptrdiff_t* strides_out,
+                          int axis, void* stream);
+
 /* Thread-local message of the last failing call on this thread ("" if none). */
 NDFB_API const char* ndfb_last_error(void);
 

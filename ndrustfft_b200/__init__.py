@@ -209,6 +209,23 @@ class Backend:
             SZ(*out_shape), PD(*out_strides), int(axis), ctypes.c_void_p(vi.stream or 0))
         self.lib.check(rc)
 
+    def ndfft_scatter_out(self, input, handler, axis, out_shape, out_strides, out_block, block_ptrs, inverse=False):
+        """ndfft / ndifft whose output blocks go to separate base pointers (ndfb_exec_scatter_out): block p of each lane is
+        written relative to `block_ptrs[p]` (ints: device addresses, e.g. peer-mapped buffers of other GPUs)."""
+        vi = _view_of(input)
+        if vi.device is None and "emu" not in self.lib.version():
+            raise ValueError("scatter-output transforms take device tensors")
+        ndim = len(vi.shape)
+        SZ = ctypes.c_size_t * ndim
+        PD = ctypes.c_ssize_t * ndim
+        PT = ctypes.c_void_p * len(block_ptrs)
+        norm = _lib.NORM_DEFAULT if handler.norm.kind == "default" else _lib.NORM_NONE
+        rc = self.lib.dll.ndfb_exec_scatter_out(
+            handler._plan, _lib.OP_IFFT if inverse else _lib.OP_FFT, norm, 1.0, int(out_block), len(block_ptrs), PT(*[int(p) for p in block_ptrs]),
+            ctypes.c_void_p(vi.ptr), ndim, SZ(*vi.shape), PD(*vi.strides), SZ(*out_shape), PD(*out_strides), int(axis),
+            ctypes.c_void_p(vi.stream or 0))
+        self.lib.check(rc)
+
     # -- Custom normalisation plumbing (host callback; SURVEY.md 7.2-7) --
     @staticmethod
     def _to_host(a):

@@ -24,7 +24,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 E_INVALID, E_SIZE_MISMATCH, E_SHAPE, E_AXIS, E_ALLOC, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
 
 EXPORTS = (
-    "ndfb_plan_create", "ndfb_plan_destroy", "ndfb_plan_describe", "ndfb_exec", "ndfb_exec_scaled", "ndfb_exec_split_out",
+    "ndfb_plan_create", "ndfb_plan_destroy", "ndfb_plan_describe", "ndfb_exec", "ndfb_exec_scaled", "ndfb_exec_split_out", "ndfb_exec_scatter_out",
     "ndfb_last_error", "ndfb_version", "ndfb_launch_count", "ndfb_release_workspaces",
 )
 
@@ -65,6 +65,8 @@ class CLib:
         d.ndfb_exec_scaled.restype = ci
         d.ndfb_exec_split_out.argtypes = [vp, ci, ci, ctypes.c_double, cz, ctypes.c_ssize_t, vp, vp, ci, szp, pdp, szp, pdp, ci, vp]
         d.ndfb_exec_split_out.restype = ci
+        d.ndfb_exec_scatter_out.argtypes = [vp, ci, ci, ctypes.c_double, cz, ci, ctypes.POINTER(vp), vp, ci, szp, pdp, szp, pdp, ci, vp]
+        d.ndfb_exec_scatter_out.restype = ci
         d.ndfb_last_error.restype = ctypes.c_char_p
         d.ndfb_version.restype = ctypes.c_char_p
         d.ndfb_launch_count.restype = ctypes.c_uint64

@@ -179,6 +179,8 @@ struct LaunchSpec {
     int fs_dim = 0;   // which batch dim carries the four-step index j2
     int os_blk = 0;   // split output axis (see TileArgs::os_blk)
     long long os_blk_stride = 0;
+    int nblk_ptr = 0;
+    void* blk_ptr[8] = {nullptr};
     ndfb_plan::FsTw fs;
     bool keep_dim_order = false;
 };
@@ -370,6 +372,8 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     }
     a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
     a.os_blk = s.os_blk; a.os_blk_stride = s.os_blk_stride;
+    a.nblk_ptr = s.nblk_ptr;
+    for (int i = 0; i < 8; ++i) a.blk_ptr[i] = s.blk_ptr[i];
     const long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
     return e->launch(a, (unsigned)grid, stream);
@@ -392,6 +396,7 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             return launch_sfft<R>(p, e, s, stream);
         }
     }
+    if (s.nblk_ptr) return fail(NDFB_E_UNSUPPORTED, "scattered output blocks need a length with an instantiated Stockham schedule");
     return launch_tile<R>(p, s, stream);
 }
 
@@ -594,6 +599,8 @@ struct OpInfo {
     const char* what = "fft";
     int os_blk = 0;
     long long os_blk_stride = 0;
+    int nblk_ptr = 0;
+    void* blk_ptr[8] = {nullptr};
 };
 
 static int op_info(const ndfb_plan* p, int op, int norm, OpInfo* o) {
@@ -709,7 +716,8 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
             s.core = c; s.in = (const char*)in + io * (long long)ie; s.out = (char*)out + oo * (long long)oe;
             s.dims = inner; s.is_axis = is_axis; s.os_axis = os_axis;
             s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-            s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride;
+            s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride; s.nblk_ptr = o.nblk_ptr;
+            for (int i = 0; i < 8; ++i) s.blk_ptr[i] = o.blk_ptr[i];
             if ((rc = (o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream)))) return rc;
         }
         return 0;
@@ -717,7 +725,8 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
     LaunchSpec s;
     s.core = c; s.in = in; s.out = out; s.dims = dims; s.is_axis = is_axis; s.os_axis = os_axis;
     s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-    s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride;
+    s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride; s.nblk_ptr = o.nblk_ptr;
+    for (int i = 0; i < 8; ++i) s.blk_ptr[i] = o.blk_ptr[i];
     return o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream);
 }
 
@@ -896,7 +905,8 @@ static int check_call(const ndfb_plan* p, const OpInfo& o, int ndim, const size_
 
 static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, ptrdiff_t out_block_stride,
                        const void* in, void* out, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
-                       const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream);
+                       const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream,
+                       int nblk_ptr = 0, void* const* blk_ptrs = nullptr);
 
 int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale, const void* in, void* out, int ndim,
                      const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
@@ -904,9 +914,21 @@ int ndfb_exec_scaled(const ndfb_plan* plan, int op, int norm, double extra_scale
     return exec_common(plan, op, norm, extra_scale, 0, 0, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
 }
 
+int ndfb_exec_scatter_out(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, int nblocks,
+                          void* const* block_ptrs, const void* in, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
+                          const size_t* shape_out, const ptrdiff_t* strides_out, int axis, void* stream) {
+    if (op != NDFB_OP_FFT && op != NDFB_OP_IFFT) return fail(NDFB_E_UNSUPPORTED, "scattered output blocks are only available for ndfft / ndifft");
+    if (!block_ptrs || nblocks < 1 || nblocks > 8) return fail(NDFB_E_INVALID, "1..8 block pointers expected");
+    if (out_block == 0 || !shape_out || axis < 0 || axis >= ndim || shape_out[axis] != out_block * (size_t)nblocks)
+        return fail(NDFB_E_INVALID, "out_block * nblocks must equal the output lane length");
+    return exec_common(plan, op, norm, extra_scale, out_block, 0, in, block_ptrs[0], ndim, shape_in, strides_in, shape_out, strides_out,
+                       axis, NDFB_MEM_DEVICE, stream, nblocks, block_ptrs);
+}
+
 static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, ptrdiff_t out_block_stride,
                        const void* in, void* out, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
-                       const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream) {
+                       const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream,
+                       int nblk_ptr, void* const* blk_ptrs) {
     if (!plan || !shape_in || !strides_in || !shape_out || !strides_out) return fail(NDFB_E_INVALID, "null argument");
     if (ndim < 1 || ndim > NDFB_MAX_DIMS) return fail(NDFB_E_INVALID, "ndim %d outside 1..%d", ndim, NDFB_MAX_DIMS);
     if (norm != NDFB_NORM_NONE && norm != NDFB_NORM_DEFAULT) return fail(NDFB_E_INVALID, "unknown norm %d", norm);
@@ -917,6 +939,8 @@ static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_sca
     if (rc) return rc;
     if ((rc = check_call(p, o, ndim, shape_in, shape_out, axis))) return rc;
     o.os_blk = (int)out_block; o.os_blk_stride = (long long)out_block_stride;
+    o.nblk_ptr = nblk_ptr;
+    for (int i = 0; i < nblk_ptr && i < 8; ++i) o.blk_ptr[i] = blk_ptrs[i];
     bool empty = false;
     for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) empty = true;
     if (empty) return NDFB_OK;

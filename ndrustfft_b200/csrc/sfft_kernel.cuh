@@ -30,6 +30,8 @@ struct SfftArgs {
     int fs_twiddle, fs_dim, fs_shift;
     int os_blk;            // != 0: output axis index k is split as (k / os_blk, k % os_blk) ...
     long long os_blk_stride;  // ... with this stride for the block index (packed all-to-all send layout)
+    int nblk_ptr;          // != 0: block p is written relative to blk_ptr[p] (peer-mapped receive buffers: the store IS the all-to-all)
+    void* blk_ptr[8];
     const void* fs_lo;
     const void* fs_hi;
 };
@@ -235,7 +237,12 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
                 if (a.fs_shift >= 40) y = cmul(y, ldg(&lo[(unsigned)ee]));
                 else y = cmul(y, cmul(ldg(&hi[ee >> a.fs_shift]), ldg(&lo[ee & ((1ull << a.fs_shift) - 1)])));
             }
-            if (a.os_blk) { out[(long long)(k / a.os_blk) * a.os_blk_stride + (long long)(k % a.os_blk) * os_axis] = y; return; }
+            if (a.os_blk) {
+                const int pblk = k / a.os_blk;
+                Cx<R>* base = a.nblk_ptr ? reinterpret_cast<Cx<R>*>(a.blk_ptr[pblk]) + lb.bo : out + (long long)pblk * a.os_blk_stride;
+                base[(long long)(k - pblk * a.os_blk) * os_axis] = y;
+                return;
+            }
         }
         out[(long long)k * os_axis] = y;
     };

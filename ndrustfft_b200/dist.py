@@ -50,7 +50,7 @@ class SlabR2cFft3d:
         for each i2-chunk c:   wait for c, ndfft along axis 0 into out[:, :, c]      (overlaps the exchange of c+1..)
     """
 
-    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=4):
+    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -80,6 +80,24 @@ class SlabR2cFft3d:
         if P > 1:
             self.send = [torch.empty(P * self.s0 * self.s1 * (hi - lo), dtype=self.ct, device=self.device) for lo, hi in self.chunks]
             self.recv = [torch.empty(P * self.s0 * self.s1 * (hi - lo), dtype=self.ct, device=self.device) for lo, hi in self.chunks]
+        # Peer mode (GPUs of one NVLink/NVSwitch node, <= 8 ranks): the receive buffers live in symmetric memory that every
+        # rank maps; the axis-1 kernel's store writes each destination's block straight into that rank's buffer
+        # (ndfb_exec_scatter_out), so there is no send buffer, no pack kernel and no NCCL call on the data path.
+        self.peer = False
+        if P > 1 and peer in ("auto", True) and getattr(self.device, "type", "cpu") == "cuda" and P <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._symm = []
+                for _ in range(2):     # double-buffered across calls (a fast rank may already scatter call t+1)
+                    buf = symm_mem.empty(P * self.s0 * self.s1 * self.m, dtype=self.ct, device=self.device)
+                    hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                    self._symm.append((buf, hdl))
+                self._call = 0
+                self.peer = True
+            except Exception as e:       # pragma: no cover - depends on the box
+                if peer is True:
+                    raise
+                self.peer_error = repr(e)
 
     # bytes each rank sends over the wire per all-to-all (for NVLink-roofline reporting)
     def bytes_sent_per_rank(self):
@@ -101,6 +119,17 @@ class SlabR2cFft3d:
         if P == 1:
             be.ndfft(self.a, self.b, self.h1, 1)
             be.ndfft(self.b, out, self.h0, 0)
+            return out
+        if self.peer:
+            buf, hdl = self._symm[self._call % 2]
+            self._call += 1
+            esz = 8 if self.rdt == np.float32 else 16
+            chunk = s0 * s1 * self.m * esz                      # my rows land in chunk `rank` of every destination
+            ptrs = [int(hdl.buffer_ptrs[p]) + self.rank * chunk for p in range(P)]
+            be.ndfft_scatter_out(self.a, self.h1, 1, out_shape=(s0, n1, self.m), out_strides=(s1 * self.m, self.m, 1),
+                                 out_block=s1, block_ptrs=ptrs)
+            hdl.barrier()                                       # every rank's stores have landed
+            be.ndfft(buf.view(n0, s1, self.m), out, self.h0, 0)
             return out
         works = []
         for c, (lo, hi) in enumerate(self.chunks):

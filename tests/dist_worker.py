@@ -32,7 +32,8 @@ def main():
     rng = np.random.default_rng(1234)
     xg = rng.uniform(-1, 1, (n0, n1, n2)).astype(dtype)        # same global array on every rank
     want = np.fft.rfftn(xg.astype(np.float64), axes=(0, 1, 2))  # = fft(axis0) . fft(axis1) . rfft(axis2)
-    plan = SlabR2cFft3d((n0, n1, n2), dtype, device=device, backend=be)
+    plan = SlabR2cFft3d((n0, n1, n2), dtype, device=device, backend=be, chunks=int(os.environ.get('NDFB_TEST_CHUNKS', '2')),
+                        peer={'auto': 'auto', 'on': True, 'off': False}[os.environ.get('NDFB_TEST_PEER', 'auto')])
     lo, hi = shard_bounds(n0, world, rank)
     x = torch.from_numpy(xg[lo:hi].copy()).to(device)
     X = plan.forward(x)
@@ -58,7 +59,7 @@ def main():
     assert not out.cpu().numpy()[:lo2].any() and not out.cpu().numpy()[hi2:].any()
     dist.barrier()
     if rank == 0:
-        print(f"DIST_OK world={world} fwd={err:.2e} back={err_b:.2e} shard={e2:.2e} sent_per_rank={plan.bytes_sent_per_rank()}")
+        print(f"DIST_OK peer={plan.peer} world={world} fwd={err:.2e} back={err_b:.2e} shard={e2:.2e} sent_per_rank={plan.bytes_sent_per_rank()}")
     dist.destroy_process_group()
 
 

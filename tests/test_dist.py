@@ -48,4 +48,11 @@ def test_slab_fft3d_nccl():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    _run("nccl", 2, (64, 64, 64), "float64", 29641)
+    out = _run("nccl", 2, (64, 64, 64), "float64", 29641)           # default: fused peer stores when symmetric memory works
+    os.environ["NDFB_TEST_PEER"] = "off"
+    try:
+        out2 = _run("nccl", 2, (64, 64, 64), "float64", 29642)      # NCCL all_to_all_single baseline path
+    finally:
+        del os.environ["NDFB_TEST_PEER"]
+    assert "peer=False" in out2
+    print(out, out2)
