@@ -72,8 +72,14 @@ class SlabR2cFft3d:
         self.h0 = self.be.FftHandler(self.n0, self.rdt, dev_index or 0)
         self.ct = torch.complex64 if self.rdt == np.float32 else torch.complex128
         self.rt = torch.float32 if self.rdt == np.float32 else torch.float64
-        self.a = torch.empty((self.s0, self.n1, self.m), dtype=self.ct, device=self.device)
-        self.b = torch.empty((self.s0, self.n1, self.m), dtype=self.ct, device=self.device)
+        # internal work arrays keep the spectrum axis padded to a multiple of 128 bytes (257 -> 264 complex f64) so that
+        # every L-lane tile row of the strided passes - and every peer store - is one aligned 128-byte line
+        lanes128 = 128 // (8 if self.rdt == np.float32 else 16)
+        self.mp = -(-self.m // lanes128) * lanes128
+        self.a_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
+        self.b_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
+        self.a = self.a_pad[:, :, :self.m]
+        self.b = self.b_pad[:, :, :self.m]
         # i2 chunks and their send / receive buffers
         k = max(1, min(int(chunks), self.m)) if P > 1 else 1
         self.chunks = [shard_bounds(self.m, k, c) for c in range(k)]
@@ -89,11 +95,17 @@ class SlabR2cFft3d:
                 import torch.distributed._symmetric_memory as symm_mem
                 self._symm = []
                 for _ in range(2):     # double-buffered across calls (a fast rank may already scatter call t+1)
-                    buf = symm_mem.empty(P * self.s0 * self.s1 * self.m, dtype=self.ct, device=self.device)
+                    buf = symm_mem.empty(P * self.s0 * self.s1 * self.mp, dtype=self.ct, device=self.device)
                     hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
                     self._symm.append((buf, hdl))
                 self._call = 0
                 self.peer = True
+                kp = max(1, int(chunks))
+                units = self.mp // lanes128
+                kp = min(kp, units)
+                self.pchunks = [tuple(lanes128 * v for v in shard_bounds(units, kp, c)) for c in range(kp)]
+                self._s1, self._s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+                self._ev = [torch.cuda.Event() for _ in range(kp)]
             except Exception as e:       # pragma: no cover - depends on the box
                 if peer is True:
                     raise
@@ -117,19 +129,41 @@ class SlabR2cFft3d:
             out = t.empty((n0, s1, self.m), dtype=self.ct, device=self.device)
         be.ndfft_r2c(x, self.a, self.h2, 2)
         if P == 1:
-            be.ndfft(self.a, self.b, self.h1, 1)
+            be.ndfft(self.a_pad, self.b_pad, self.h1, 1)        # padded lanes: 264 per row, tiles never straddle rows
             be.ndfft(self.b, out, self.h0, 0)
             return out
         if self.peer:
             buf, hdl = self._symm[self._call % 2]
             self._call += 1
             esz = 8 if self.rdt == np.float32 else 16
-            chunk = s0 * s1 * self.m * esz                      # my rows land in chunk `rank` of every destination
+            mp = self.mp
+            chunk = s0 * s1 * mp * esz                          # my rows land in chunk `rank` of every destination
             ptrs = [int(hdl.buffer_ptrs[p]) + self.rank * chunk for p in range(P)]
-            be.ndfft_scatter_out(self.a, self.h1, 1, out_shape=(s0, n1, self.m), out_strides=(s1 * self.m, self.m, 1),
-                                 out_block=s1, block_ptrs=ptrs)
-            hdl.barrier()                                       # every rank's stores have landed
-            be.ndfft(buf.view(n0, s1, self.m), out, self.h0, 0)
+            recv = buf.view(n0, s1, mp)
+            K = len(self.pchunks)
+            if K == 1:
+                be.ndfft_scatter_out(self.a_pad, self.h1, 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1),
+                                     out_block=s1, block_ptrs=ptrs)
+                hdl.barrier()                                   # every rank's stores have landed
+                be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
+                return out
+            # pieces of the (padded) spectrum axis: the NVLink-bound scatter of piece c+1 runs on one stream while the
+            # HBM-bound axis-0 pass of piece c runs on another
+            main = t.cuda.current_stream(self.device)
+            self._s1.wait_stream(main)
+            for c, (lo, hi) in enumerate(self.pchunks):
+                with t.cuda.stream(self._s1):
+                    be.ndfft_scatter_out(self.a_pad[:, :, lo:hi], self.h1, 1, out_shape=(s0, n1, hi - lo),
+                                         out_strides=(s1 * mp, mp, 1), out_block=s1,
+                                         block_ptrs=[q + lo * esz for q in ptrs])
+                    hdl.barrier(channel=c)
+                    self._ev[c].record(self._s1)
+                with t.cuda.stream(self._s2):
+                    self._s2.wait_event(self._ev[c])
+                    hi_m = min(hi, self.m)
+                    if hi_m > lo:
+                        be.ndfft(recv[:, :, lo:hi_m], out[:, :, lo:hi_m], self.h0, 0)
+            main.wait_stream(self._s2)
             return out
         works = []
         for c, (lo, hi) in enumerate(self.chunks):
