@@ -270,17 +270,25 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        worst = max(range(4), key=lambda i: per[i])
-        ach = BYTES_PER_TRANSFORM / (per[worst] * 1e-3) / 1e9
+        # Dominant kernel = the one with the largest share of the step.  The two contiguous-axis calls are ONE launch each of
+        # the 8192-point row kernel (2 launches/step); each strided-axis call is two launches (64-point and 128-point
+        # column passes of the two-pass decomposition), every one of them moving 1 GiB.  Shares are in `launches`.
+        rows_ms = 0.5 * (per[0] + per[3])
+        worst = 0
+        ach = BYTES_PER_TRANSFORM / (rows_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "c2: 8192x8192 c64 ndfft axis1, ndfft axis0, ndifft axis0, ndifft axis1 (one step = 4 axis transforms)",
                        "l2": "inputs larger than L2 (512 MiB per array, 3 arrays cycled)", "sharding": "independent array per rank, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "tile_kernel<float,false>: " + STEP_NAMES[worst], "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_TRANSFORM},
+            "roofline": {"bound": "hbm", "kernel": "sfft_kernel<float, Sched<8192,...>, rows> (ndfft/ndifft along the contiguous axis: one launch per call)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": 1.027e9, "traffic_source": "ncu --set full, profiles/r1h_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 490 MB per launch",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_TRANSFORM,
+                         "share_of_step": (per[0] + per[3]) / sum(per),
+                         "strided_axis_call": {"launches_per_call": 2, "ms": 0.5 * (per[1] + per[2]),
+                                               "frac_of_one_pass_bytes": BYTES_PER_TRANSFORM / (0.5 * (per[1] + per[2]) * 1e-3) / 1e9 / peak}},
             "launches": [{"name": STEP_NAMES[i], "ms": per[i], "GB/s": BYTES_PER_TRANSFORM / (per[i] * 1e-3) / 1e9,
                           "frac": BYTES_PER_TRANSFORM / (per[i] * 1e-3) / 1e9 / peak,
                           "GFLOP/s": FLOPS_PER_TRANSFORM / (per[i] * 1e-3) / 1e9} for i in range(4)],

@@ -410,6 +410,18 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
 #include "rsfft_tables.inc"
     };
 #undef RSFFT_TABLE
+    if (const char* pick = std::getenv("NDFB_RSFFT_PICK")) {   // measurement hook, as NDFB_SFFT_PICK
+        int pn = 0, pi = 0;
+        if (sscanf(pick, "%d:%d", &pn, &pi) == 2 && pn == N) {
+            int seen = 0;
+            for (const Tab& t : tabs)
+                for (int i = 0; i < t.n; ++i) {
+                    const RsfftEntry* e = &t.e[i];
+                    if (e->f64 != (f64 ? 1 : 0) || e->kind != rkind || e->N != N || e->cols != (cols ? 1 : 0)) continue;
+                    if (seen++ == pi) return e;
+                }
+        }
+    }
     const int pref = preferred_family(f64, N, cols, true);
     const RsfftEntry* best = nullptr;
     for (const Tab& t : tabs)

@@ -116,7 +116,7 @@ def c2c_cols(f64):
                 if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
                     continue
                 cand.append(e)
-            out.extend(cand[:2])  # the two widest tiles that fit
+            out.extend(cand[:3])  # the three widest tiles that fit
     return dedup(out)
 
 
@@ -138,6 +138,7 @@ def real_entries(f64):
             if sc is None:
                 continue
             TL, rad = sc
+            nfit = 0
             for L in (32, 16, 8, 4, 2):
                 if L * rs > 128:
                     continue
@@ -145,7 +146,9 @@ def real_entries(f64):
                 if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
                     continue
                 out.append(e)
-                break
+                nfit += 1
+                if nfit == 2:
+                    break
     return dedup(out)
 
 
