@@ -208,8 +208,9 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0)
 // ------------------------------------------------------------------------------------------------------
 // complex-to-complex
 // ------------------------------------------------------------------------------------------------------
-// PLAIN: no four-step twiddle and no split output axis;  UNIT: both axis strides are 1 (contiguous rows)
-template <typename R, class S, int L, bool COLS, bool PLAIN, bool UNIT>
+// MODE 0: plain store;  1: four-step twiddle from the single table W_N^e (N <= 2^17), nothing else;  2: everything
+// (hi/lo twiddle product, split / scattered output blocks).  UNIT: both axis strides are 1 (contiguous rows)
+template <typename R, class S, int L, bool COLS, int MODE, bool UNIT>
 NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, const LaneBase& lb) {
     const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
     Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
@@ -229,7 +230,9 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     auto store = [&](int k, Cx<R> val) {
         if (!valid) return;
         Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
-        if (!PLAIN) {
+        if (MODE == 1) {
+            y = cmul(y, ldg(&reinterpret_cast<const Cx<R>*>(a.fs_lo)[(unsigned)k * (unsigned)j2]));
+        } else if (MODE == 2) {
             if (a.fs_twiddle) {
                 const Cx<R>* lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
                 const Cx<R>* hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
@@ -261,9 +264,10 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     c.valid = g < a.nlanes;
     const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
     const bool plain = !a.fs_twiddle && !a.os_blk;
-    if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, true, true>(a, c, lb);
-    else if (plain) sfft_body<R, S, L, COLS, true, false>(a, c, lb);
-    else sfft_body<R, S, L, COLS, false, false>(a, c, lb);
+    if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, 0, true>(a, c, lb);
+    else if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb);
+    else if (a.fs_twiddle && a.fs_shift >= 40 && !a.os_blk) sfft_body<R, S, L, COLS, 1, false>(a, c, lb);
+    else sfft_body<R, S, L, COLS, 2, false>(a, c, lb);
 }
 
 // ------------------------------------------------------------------------------------------------------

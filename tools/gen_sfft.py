@@ -25,6 +25,8 @@ MIXED = {  # N: (TL, radices)   ({2,3,5}-smooth lengths of BASELINE config c5a a
     60: (10, [6, 10]),
     216: (36, [6, 6, 6]),
     600: (100, [6, 10, 10]),
+    264: (33, [8, 3, 11]),        # benches/ndrustfft.rs FFT_SIZES / DCT_SIZES (264, 265): 2^3 3 11
+    132: (33, [4, 3, 11]),        # core of the 264-point r2c
     81: (9, [9, 9]),
     729: (81, [9, 9, 9]),
     4095: (512, [13, 9, 7, 5]),   # DCT-I of 4096 points (BASELINE c4): core 4095 = 3^2 5 7 13
@@ -125,7 +127,7 @@ def real_entries(f64):
     rs = 8 if f64 else 4
     cs = 2 * rs
     for fam in (0, 1):
-        for N in [64, 128, 256, 512, 1024, 2048, 4096, 4095]:
+        for N in [64, 128, 256, 512, 1024, 2048, 4096, 4095, 132, 264]:
             sc = schedule(N, f64, fam)
             if sc is None:
                 continue
@@ -133,7 +135,7 @@ def real_entries(f64):
             if TL < 2 or TL > 512:
                 continue
             out.append(make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam, always_smem=True))
-        for N in [32, 64, 128, 256, 512, 1024, 2048, 4096]:
+        for N in [32, 64, 128, 256, 512, 1024, 2048, 4096, 132, 264]:
             sc = schedule(N, f64, fam)
             if sc is None:
                 continue
