@@ -20,6 +20,7 @@
 #include "common.h"
 #include "devapi.h"
 #include "plan.h"
+#include "big_kernels.cuh"
 #include "sfft_inst.h"
 #include "tile_kernel.cuh"
 
@@ -69,6 +70,9 @@ struct ndfb_plan {
     // four-step inter-pass twiddles, keyed by total length
     struct FsTw { void *lo = nullptr, *hi = nullptr; int shift = 0; };
     std::map<long long, FsTw> fs;
+    // staged Bluestein (lengths with a large prime factor that do not fit one CTA): chirp c[j] and FFT_M(kernel)/M
+    struct BigBlu { void *chirp = nullptr, *bhat = nullptr; int M = 0; };
+    std::map<long long, BigBlu> bigblu;
 };
 
 namespace ndfb {
@@ -136,7 +140,7 @@ static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
 // ------------------------------------------------------------------------------------------------------
 struct Pool {
     struct Slot { void* p = nullptr; size_t bytes = 0; int device = -1; };
-    Slot slots[3];
+    Slot slots[5];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows
     ~Pool() {}  // device memory is reclaimed at process exit; explicit release via ndfb_release_workspaces
     int get(int which, int device, size_t bytes, void** out) {
         Slot& s = slots[which];
@@ -197,26 +201,42 @@ static int preferred_family(bool f64, int N, bool cols, bool real_kind) {
     return 1;
 }
 
+// resident threads per SM this entry can expect (registers estimated from the points per thread)
 template <typename E>
-static bool better_entry(const E* e, const E* best, long long nlanes, int pref_fam, size_t lane_elem_bytes) {
+static int resident_threads(const E* e) {
+    const int regs = e->f64 ? e->E * 4 + (e->fam == 1 ? 32 : 56) : e->E * 2 + (e->fam == 1 ? 32 : 44);
+    int ctas = 65536 / (e->threads * (regs < 32 ? 32 : regs));
+    if (e->smem) ctas = std::min<int>(ctas, (int)((227 * 1024) / e->smem));
+    ctas = std::min(ctas, 2048 / e->threads);
+    ctas = std::max(1, std::min(ctas, 32));
+    return ctas * e->threads;
+}
+
+template <typename E>
+static bool better_entry(const E* e, const E* best, long long nlanes, int pref_fam, size_t lane_elem_bytes, long long axis_stride_bytes) {
     if (!best) return true;
     // 0. strided tiles must cover at least one 32-byte sector per row
     if (e->cols) {
         const bool e_sec = (size_t)e->L * lane_elem_bytes >= 32, b_sec = (size_t)best->L * lane_elem_bytes >= 32;
         if (e_sec != b_sec) return e_sec;
     }
-    // 1. a tile not much wider than the batch, 2. the preferred family, 3. a tile that lets two CTAs share an SM,
-    // 4. the widest tile
+    // 1. a tile not much wider than the batch, 2. the preferred family
     const bool e_fit = e->L <= 2 * nlanes, b_fit = best->L <= 2 * nlanes;
     if (e_fit != b_fit) return e_fit;
     const bool e_f = e->fam == pref_fam, b_f = best->fam == pref_fam;
     if (e_f != b_f) return e_f;
-    const bool e_ok = e->smem <= 112 * 1024, b_ok = best->smem <= 112 * 1024;
-    if (e_ok != b_ok) return e_ok;
+    // 3. rows more than ~1 MiB apart (one 2 MiB page per few rows): the widest tile amortises the TLB misses
+    //    (c3 axis 0, L = 4 vs 8: 0.63 vs 0.47 ms); otherwise occupancy decides (1000-point f64 columns, L = 2 vs 4:
+    //    0.528 vs 0.453 of the roofline), ties go to the wider tile
+    if (e->cols && axis_stride_bytes >= (1 << 20)) {
+        if (e->L != best->L) return e->L > best->L;
+    }
+    const int er = resident_threads(e), br = resident_threads(best);
+    if (er != br) return er > br;
     return e->L > best->L;
 }
 
-static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes) {
+static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes, long long axis_stride_bytes = 0) {
     static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
     if (disabled) return nullptr;
     const SfftEntry* tabs[4] = {kSfft_f32_rows, kSfft_f32_cols, kSfft_f64_rows, kSfft_f64_cols};
@@ -236,7 +256,7 @@ static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes) 
     for (int i = 0; i < counts[which]; ++i) {
         const SfftEntry* e = &tabs[which][i];
         if (e->N != N) continue;
-        if (better_entry(e, best, nlanes, pref, f64 ? (size_t)16 : (size_t)8)) best = e;
+        if (better_entry(e, best, nlanes, pref, f64 ? (size_t)16 : (size_t)8, axis_stride_bytes)) best = e;
     }
     return best;
 }
@@ -389,7 +409,7 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         const bool have_batch = !s.dims.empty() && nlanes > 1;
         const bool cols = have_batch && t.N > 1 &&
                           (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
-        const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes);
+        const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
             if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
@@ -401,7 +421,7 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
 }
 
 // ---- real-transform fast path ----
-static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long long nlanes) {
+static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long long nlanes, long long axis_stride_bytes = 0) {
     static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
     if (disabled) return nullptr;
     struct Tab { const RsfftEntry* e; int n; };
@@ -428,7 +448,7 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
         for (int i = 0; i < t.n; ++i) {
             const RsfftEntry* e = &t.e[i];
             if (e->f64 != (f64 ? 1 : 0) || e->kind != rkind || e->N != N || e->cols != (cols ? 1 : 0)) continue;
-            if (better_entry(e, best, nlanes, pref, f64 ? (size_t)8 : (size_t)4)) best = e;
+            if (better_entry(e, best, nlanes, pref, f64 ? (size_t)8 : (size_t)4, axis_stride_bytes)) best = e;
         }
     return best;
 }
@@ -467,7 +487,7 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
                 for (auto& d : s.dims) if (d.os % 2) ok = false;
             }
         }
-        const RsfftEntry* e = ok ? find_rsfft(sizeof(R) == 8, rk, t.N, cols, nlanes) : nullptr;
+        const RsfftEntry* e = ok ? find_rsfft(sizeof(R) == 8, rk, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(R)) : nullptr;
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
             if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
@@ -653,6 +673,173 @@ static int op_info(const ndfb_plan* p, int op, int norm, OpInfo* o) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// staged path: prologue kernel -> complex core on workspace rows -> epilogue kernel (big_kernels.cuh)
+// ------------------------------------------------------------------------------------------------------
+struct BigMulArgs { void* ws; const void* bhat; long long ldw, nchunk; int M; };
+template <typename R>
+__global__ void __launch_bounds__(256) big_mul_entry(const __grid_constant__ BigMulArgs a) {
+    Cx<R>* __restrict__ ws = reinterpret_cast<Cx<R>*>(a.ws);
+    const Cx<R>* __restrict__ bhat = reinterpret_cast<const Cx<R>*>(a.bhat);
+    const long long total = a.nchunk * (long long)a.M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long lane = idx / a.M;
+        const int k = (int)(idx - lane * a.M);
+        Cx<R>* q = &ws[lane * a.ldw + k];
+        *q = cconj(cmul(*q, ldg(&bhat[k])));
+    }
+}
+
+// forward C2C of `rows` contiguous rows of length N (N smooth): one tile per row if it fits, else four-step
+template <typename R>
+static int c2c_rows(ndfb_plan* p, long long N, const void* in, void* out, long long rows, long long ld, stream_t stream) {
+    const size_t cs = sizeof(Cx<R>);
+    const size_t cap = dev_smem_cap(p->device) - 1024;
+    if ((size_t)N * cs + 64 <= cap && !std::getenv("NDFB_FORCE_FOUR_STEP")) {
+        Core* c = get_core(p, TK_C2C, (int)N);
+        int rc = ensure_device<R>(p, c);
+        if (rc) return rc;
+        LaunchSpec s;
+        s.core = c; s.in = in; s.out = out;
+        s.dims.push_back({rows, ld, ld});
+        s.is_axis = 1; s.os_axis = 1;
+        return launch_c2c<R>(p, s, stream);
+    }
+    std::vector<BDim> dims;
+    dims.push_back({rows, ld, ld});
+    return exec_four_step<R>(p, N, false, 1.0, in, out, dims, 1, 1, stream);
+}
+
+// host FFT (iterative radix 2, double) for the Bluestein kernel spectrum of the staged path
+static void host_fft_pow2(std::vector<std::complex<double>>& x) {
+    const size_t n = x.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(x[i], x[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        std::vector<std::complex<double>> w(len / 2);
+        for (size_t k = 0; k < len / 2; ++k) { cld u = unit_root((long long)k, (long long)len); w[k] = std::complex<double>((double)u.real(), (double)u.imag()); }
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const std::complex<double> a = x[i + k], b = x[i + k + len / 2] * w[k];
+                x[i + k] = a + b;
+                x[i + k + len / 2] = a - b;
+            }
+    }
+}
+
+template <typename R>
+static int get_big_bluestein(ndfb_plan* p, long long N, ndfb_plan::BigBlu* out) {
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->bigblu.find(N);
+    if (it != p->bigblu.end()) { *out = it->second; return 0; }
+    long long M = 1;
+    while (M < 2 * N - 1) M <<= 1;
+    if (M > (1LL << 26)) return fail(NDFB_E_UNSUPPORTED, "length %lld needs a %lld-point Bluestein convolution: too long", N, M);
+    std::vector<cld> chirp(N);
+    for (long long j = 0; j < N; ++j) chirp[j] = unit_root((j * j) % (2 * N), 2 * N);
+    std::vector<std::complex<double>> b(M, std::complex<double>(0, 0));
+    for (long long j = 0; j < N; ++j) {
+        std::complex<double> v((double)chirp[j].real(), -(double)chirp[j].imag());
+        b[j] = v;
+        if (j > 0) b[M - j] = v;
+    }
+    host_fft_pow2(b);
+    std::vector<cld> bh(M);
+    for (long long k = 0; k < M; ++k) bh[k] = cld(b[k].real() / (double)M, b[k].imag() / (double)M);
+    ndfb_plan::BigBlu t;
+    t.M = (int)M;
+    int rc;
+    if ((rc = dev_set(p->device))) return rc;
+    if ((rc = upload_cx<R>(&t.chirp, chirp))) return rc;
+    if ((rc = upload_cx<R>(&t.bhat, bh))) return rc;
+    p->bigblu[N] = t;
+    *out = t;
+    return 0;
+}
+
+template <typename R>
+static int exec_big(ndfb_plan* p, const OpInfo& o, double scale, const void* in, void* out, std::vector<BDim> dims,
+                    long long is_axis, long long os_axis, stream_t stream) {
+    const size_t cs = sizeof(Cx<R>);
+    const int bk = o.tk == TK_C2C ? (int)BK_C2C : rkind_of(o.tk);
+    if (bk < 0) return fail(NDFB_E_UNSUPPORTED, "%s of odd length %zu does not fit one CTA's shared memory; the staged path covers complex and even-length real transforms", o.what, p->n);
+    const long long n = (long long)p->n;
+    const long long N = o.tk == TK_C2C ? n : (o.tk == TK_DCT1 ? n - 1 : n / 2);
+    if (N < 1) return fail(NDFB_E_UNSUPPORTED, "length too short for the staged path");
+    normalize_dims(dims);
+    if ((int)dims.size() > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "staged transform with more than %d batch dims", kMaxBatchDims);
+    long long nlanes = 1;
+    for (auto& d : dims) nlanes *= d.size;
+    if (nlanes == 0) return 0;
+    int rc;
+    // kind tables (tabA / tabB) without the single-tile tables
+    Core* kc = nullptr;
+    if (o.tk != TK_C2C) {
+        std::lock_guard<std::mutex> g(p->mu);
+        auto key = std::make_pair(o.tk + 1000, (int)n);
+        auto it = p->cores.find(key);
+        if (it == p->cores.end()) {
+            std::unique_ptr<Core> c(new Core());
+            build_core(c->t, o.tk, (int)n, /*tables_only=*/true);
+            kc = c.get();
+            p->cores[key] = std::move(c);
+        } else kc = it->second.get();
+    }
+    if (kc && (rc = ensure_device<R>(p, kc))) return rc;
+    ndfb_plan::BigBlu blu;
+    const bool bluestein = !is_smooth(N);
+    if (bluestein && (rc = get_big_bluestein<R>(p, N, &blu))) return rc;
+    const long long rowlen = bluestein ? blu.M : N;
+    const long long budget = 1LL << 30;   // bytes per workspace buffer
+    long long chunk = std::max<long long>(1, budget / (rowlen * (long long)cs));
+    chunk = std::min(chunk, nlanes);
+    void *w1 = nullptr, *w2 = nullptr;
+    if ((rc = g_pool.get(3, p->device, (size_t)(chunk * rowlen) * cs, &w1))) return rc;
+    if ((rc = g_pool.get(4, p->device, (size_t)(chunk * rowlen) * cs, &w2))) return rc;
+    {
+        const bool trace = std::getenv("NDFB_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[ndfb] staged kind=%d n=%lld core N=%lld %s rowlen=%lld lanes=%lld chunk=%lld\n", bk, n, N, bluestein ? "bluestein" : "direct", rowlen, nlanes, chunk);
+    }
+    BigArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.in = in; a.out = out; a.ldw = rowlen; a.nlanes = nlanes;
+    a.nbd = (int)dims.size();
+    for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = dims[d].size; a.bis[d] = dims[d].is; a.bos[d] = dims[d].os; }
+    a.is_axis = is_axis; a.os_axis = os_axis;
+    a.kind = bk; a.n = (int)n; a.N = (int)N; a.M = bluestein ? blu.M : 0; a.n_out = (int)o.n_out;
+    a.conj_in = o.conj_in; a.conj_out = o.conj_out; a.scale = scale;
+    a.tabA = kc ? kc->d.tabA : nullptr; a.tabB = kc ? kc->d.tabB : nullptr;
+    a.chirp = blu.chirp;
+    const int sms = dev_sm_count(p->device);
+    for (long long l0 = 0; l0 < nlanes; l0 += chunk) {
+        const long long nc = std::min(chunk, nlanes - l0);
+        a.lane0 = l0; a.nchunk = nc;
+        a.ws = w1;
+        unsigned grid = (unsigned)std::min<long long>((nc * rowlen + 255) / 256, (long long)sms * 16);
+        if ((rc = dev_launch(big_pro_kernel<R>, grid, 256, 0, stream, a))) return rc;
+        const void* result = nullptr;
+        if (!bluestein) {
+            if ((rc = c2c_rows<R>(p, N, w1, w2, nc, rowlen, stream))) return rc;
+            result = w2;
+        } else {
+            if ((rc = c2c_rows<R>(p, rowlen, w1, w2, nc, rowlen, stream))) return rc;
+            BigMulArgs m{w2, blu.bhat, rowlen, nc, blu.M};
+            if ((rc = dev_launch(big_mul_entry<R>, grid, 256, 0, stream, m))) return rc;
+            if ((rc = c2c_rows<R>(p, rowlen, w2, w1, nc, rowlen, stream))) return rc;
+            result = w1;
+        }
+        a.ws = const_cast<void*>(result);
+        grid = (unsigned)std::min<long long>((nc * (long long)a.n_out + 255) / 256, (long long)sms * 16);
+        if ((rc = dev_launch(big_epi_kernel<R>, grid, 256, 0, stream, a))) return rc;
+    }
+    return 0;
+}
+
 template <typename R>
 static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, int ndim,
                        const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
@@ -707,10 +894,11 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         if (!fits_one_tile(p, c->t, cs)) single = false;
     }
     if (!single && o.os_blk) return fail(NDFB_E_UNSUPPORTED, "split output axis is only available for single-pass complex transforms");
+    if (single && !o.os_blk && std::getenv("NDFB_FORCE_STAGED") && (o.tk == TK_C2C || rkind_of(o.tk) >= 0) && p->n >= 4) single = false;
     if (!single) {
-        if (o.tk != TK_C2C)
-            return fail(NDFB_E_UNSUPPORTED, "%s of length %zu does not fit one CTA's shared memory; only complex-to-complex has a multi-pass path in this build", o.what, p->n);
-        return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, in, out, dims, is_axis, os_axis, stream);
+        if (o.tk == TK_C2C && is_smooth((long long)p->n) && !std::getenv("NDFB_FORCE_STAGED"))
+            return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, in, out, dims, is_axis, os_axis, stream);
+        return exec_big<R>(p, o, scale, in, out, dims, is_axis, os_axis, stream);
     }
     if ((rc = ensure_device<R>(p, c))) return rc;
     normalize_dims(dims);
@@ -897,6 +1085,7 @@ void ndfb_plan_destroy(ndfb_plan* p) {
         for (auto& kv2 : d.sfft_tw) if (kv2.second) dev_free(kv2.second);
     }
     for (auto& kv : p->fs) { if (kv.second.lo) dev_free(kv.second.lo); if (kv.second.hi) dev_free(kv.second.hi); }
+    for (auto& kv : p->bigblu) { if (kv.second.chirp) dev_free(kv.second.chirp); if (kv.second.bhat) dev_free(kv.second.bhat); }
     delete p;
 }
 
@@ -999,7 +1188,8 @@ size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {
         if (o.tk == TK_DCT1) N_est = (long long)p->n - 1;
         if (p->n == 0 || (o.tk == TK_DCT1 && p->n < 2)) { s += ",\"family\":\"empty\"}"; continue; }
         if ((size_t)N_est * cs + 64 > 226 * 1024) {
-            s += std::string(",\"family\":\"") + (o.tk == TK_C2C && is_smooth((long long)p->n) ? "four-step" : "unsupported") + "\",\"N\":" + std::to_string(N_est) + "}";
+            const bool staged_ok = o.tk == TK_C2C || rkind_of(o.tk) >= 0;
+            s += std::string(",\"family\":\"") + (o.tk == TK_C2C && is_smooth((long long)p->n) ? "four-step" : (staged_ok ? "staged" : "unsupported")) + "\",\"N\":" + std::to_string(N_est) + "}";
             continue;
         }
         Core* c = get_core(p, o.tk, (int)p->n);

@@ -112,7 +112,7 @@ struct CoreTables {
     std::vector<uint32_t> perm;
 };
 
-inline void build_core(CoreTables& t, int kind, int n) {
+inline void build_core(CoreTables& t, int kind, int n, bool tables_only = false) {
     t.kind = kind;
     t.n = n;
     const int m = n / 2 + 1;
@@ -128,7 +128,10 @@ inline void build_core(CoreTables& t, int kind, int n) {
         case TK_DCT4_ODD: t.N = 2 * n; t.n_in = n; t.n_out = n; break;
     }
     const int N = t.N;
-    if (N <= 1 || factorize(N, t.radix)) {
+    if (tables_only) {
+        // staged path: only the kind's pre/post tables are needed (the core runs as separate launches)
+        t.M = 0; t.B = 0; t.radix.clear();
+    } else if (N <= 1 || factorize(N, t.radix)) {
         if (N <= 1) t.radix.clear();
         t.M = 0;
         t.B = N;
@@ -148,8 +151,10 @@ inline void build_core(CoreTables& t, int kind, int n) {
         for (auto& v : b) v /= (long double)t.M;
         t.blu_bhat = std::move(b);
     }
-    t.tw.resize(t.B > 0 ? t.B : 1);
-    for (int k = 0; k < t.B; ++k) t.tw[k] = unit_root(k, t.B);
+    if (!tables_only) {
+        t.tw.resize(t.B > 0 ? t.B : 1);
+        for (int k = 0; k < t.B; ++k) t.tw[k] = unit_root(k, t.B);
+    }
     // lane slots: the core buffer, plus the one extra bin the "zip" kinds read
     t.Bl = t.B;
     if (kind == TK_C2R_EVEN || kind == TK_DCT3_EVEN) t.Bl = std::max(t.Bl, N + 1);

@@ -321,3 +321,32 @@ def test_scatter_output_blocks(hs):
     want = np.fft.fft(x, axis=1)
     for p in range(P):
         assert orc.rel_l2(bufs[p], want[:, p * s1:(p + 1) * s1, :]) < 1e-12
+
+
+# ---- staged path (big_kernels.cuh): prologue kernel -> complex core on workspace rows -> epilogue kernel ----
+@pytest.mark.parametrize("op", ["ndfft", "ndifft", "ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4"])
+@pytest.mark.parametrize("n", [64, 90, 202, 1018])     # smooth, smooth, 2*101 (Bluestein core), 2*509
+def test_staged_path(hs, op, n, capfd):
+    """Lengths that overflow one CTA's shared memory take the staged route; NDFB_FORCE_STAGED runs it at test sizes."""
+    import os
+    nn = n + 1 if op == "nddct1" else n
+    os.environ["NDFB_FORCE_STAGED"] = "1"
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run(op, nn, (3, nn), 1, np.float64, seed=n)
+        hs.run(op, nn, (nn, 5), 0, np.float32, seed=n + 1, norm="none")
+    finally:
+        del os.environ["NDFB_FORCE_STAGED"]
+        del os.environ["NDFB_TRACE"]
+    assert capfd.readouterr().err.count("[ndfb] staged") == 2
+
+
+def test_staged_path_prime_c2c(hs):
+    import os
+    os.environ["NDFB_FORCE_STAGED"] = "1"
+    try:
+        hs.run("ndfft", 1009, (2, 1009), 1, np.float64, seed=1)
+        hs.run("ndifft", 257, (257, 3), 0, np.float64, seed=2)
+        hs.run("ndfft", 97, (4, 97, 2), 1, np.float32, seed=3)
+    finally:
+        del os.environ["NDFB_FORCE_STAGED"]

@@ -354,3 +354,25 @@ def test_config5b_2pow24_c64_batch64(dev):
     back = torch.empty_like(x)
     be.ndifft(y, back, h, 1)
     assert _rel(back, x) < 1e-5
+
+
+# ---- staged path at sizes that really overflow one CTA (real kinds, large primes) ----
+@pytest.mark.parametrize("op,n,rd", [("ndfft_r2c", 1 << 18, np.float64), ("ndifft_r2c", 1 << 18, np.float32),
+                                      ("nddct2", 1 << 16, np.float64), ("nddct3", 1 << 16, np.float64),
+                                      ("nddct4", 40000, np.float32), ("nddct1", 32769, np.float64),
+                                      ("ndfft", 65537, np.float64), ("ndifft", 1000003, np.float32),
+                                      ("ndfft_r2c", 2 * 10007, np.float64)])
+def test_staged_long_lanes(dev, op, n, rd):
+    dev.run(op, n, (3, n), 1, rd, seed=n % 977)
+    if n <= (1 << 16):
+        dev.run(op, n, (n, 4), 0, rd, seed=n % 977 + 1)
+
+
+def test_plan_families_reported(dev):
+    be = dev.be
+    fam = lambda h: [o["family"] for o in h.describe()["ops"]]
+    assert fam(be.FftHandler(8192, np.float32)) == ["direct", "direct"]
+    assert fam(be.FftHandler(1 << 24, np.float32))[0] == "four-step"
+    assert fam(be.FftHandler(1000003, np.float32))[0] == "staged"
+    assert fam(be.R2cFftHandler(1 << 20))[0] == "staged"
+    assert fam(be.FftHandler(1009))[0] == "bluestein"
