@@ -131,6 +131,10 @@ NDFB_API const char* ndfb_version(void);
  * `gpu_launches`. */
 NDFB_API uint64_t ndfb_launch_count(void);
 
+/* Occupancy hint for the NEXT kernel launch of the calling thread: request at least `bytes` of dynamic shared memory
+ * (e.g. 116 KiB => one CTA per SM), so that a link-bound kernel leaves room for another stream's HBM-bound kernel. */
+NDFB_API void ndfb_hint_next_launch_smem(size_t bytes);
+
 /* Release cached workspaces / pinned staging buffers held by the calling thread's pools. */
 NDFB_API void ndfb_release_workspaces(void);
 

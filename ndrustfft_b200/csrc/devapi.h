@@ -30,6 +30,7 @@ inline int fail(int code, const char* fmt, ...) {
 }
 
 std::atomic<uint64_t>& launch_counter();  // defined in ndfft_b200.cu
+size_t& launch_smem_floor();               // thread-local, consumed by the next launch (occupancy hint); ndfft_b200.cu
 
 // ------------------------------------------------------------------------------------------------------
 // device plumbing (CUDA, or plain host memory in the emulation build)
@@ -90,6 +91,11 @@ inline int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stre
     if (it == attr_set.end() || it->second < smem) {
         NDFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set[key] = 227 * 1024;
+    }
+    {
+        size_t& floor_ = launch_smem_floor();
+        if (floor_ > smem) smem = floor_ < (size_t)(227 * 1024) ? floor_ : (size_t)(227 * 1024);
+        floor_ = 0;
     }
     kernel<<<grid, block, smem, s>>>(a);
     NDFB_CUDA(cudaGetLastError());

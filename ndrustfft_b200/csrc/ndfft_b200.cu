@@ -30,6 +30,8 @@ static thread_local std::string g_err;
 std::string& err_slot() { return g_err; }
 static std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t>& launch_counter() { return g_launches; }
+static thread_local size_t g_smem_floor = 0;
+size_t& launch_smem_floor() { return g_smem_floor; }
 
 // ------------------------------------------------------------------------------------------------------
 // plans
@@ -984,7 +986,8 @@ static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale
     if (total_in + total_out < (size_t)(16u << 20)) return 0;
     const int d = axis == 0 ? 1 : 0;               // split dim: outermost non-transformed dim
     const size_t nd = shape_in[d];
-    int K = 8;
+    int K = HostPipe::kMaxChunks;   // 16 pieces: fill + drain of the three-stage pipeline cost 2/16 of a transfer
+    if (const char* e = std::getenv("NDFB_HOST_CHUNKS")) K = std::max(2, std::min(HostPipe::kMaxChunks, atoi(e)));
     while (K > 1 && (nd / K < 1 || (total_in / K) < (size_t)(2u << 20))) K /= 2;
     if (K < 2 || nd < (size_t)K) return 0;
     int rc = g_pipe.init(p->device);
@@ -1207,6 +1210,7 @@ size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {
     return s.size() + 1;
 }
 
+void ndfb_hint_next_launch_smem(size_t bytes) { launch_smem_floor() = bytes; }
 const char* ndfb_last_error(void) { return g_err.c_str(); }
 const char* ndfb_version(void) { return version_string(); }
 uint64_t ndfb_launch_count(void) { return g_launches.load(); }

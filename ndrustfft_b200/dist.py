@@ -50,7 +50,8 @@ class SlabR2cFft3d:
         for each i2-chunk c:   wait for c, ndfft along axis 0 into out[:, :, c]      (overlaps the exchange of c+1..)
     """
 
-    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto"):
+    def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto",
+                 row_chunks=1, scatter_smem=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -105,7 +106,12 @@ class SlabR2cFft3d:
                 kp = min(kp, units)
                 self.pchunks = [tuple(lanes128 * v for v in shard_bounds(units, kp, c)) for c in range(kp)]
                 self._s1, self._s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
-                self._ev = [torch.cuda.Event() for _ in range(kp)]
+                self._ev = [torch.cuda.Event() for _ in range(max(kp, int(row_chunks)) + 1)]
+                # row-chunked overlap: r2c of row chunk c+1 (HBM-bound) runs beside the scatter of chunk c (NVLink-bound);
+                # the scatter launch is capped to ~1 CTA/SM through a shared-memory floor so the other stream gets SM room
+                kr = max(1, min(int(row_chunks), self.s0))
+                self.rchunks = [shard_bounds(self.s0, kr, c) for c in range(kr)]
+                self.scatter_smem = (116 * 1024 if P >= 4 else 0) if scatter_smem is None else int(scatter_smem)
             except Exception as e:       # pragma: no cover - depends on the box
                 if peer is True:
                     raise
@@ -127,7 +133,8 @@ class SlabR2cFft3d:
         assert tuple(x.shape) == (s0, n1, self.n2), x.shape
         if out is None:
             out = t.empty((n0, s1, self.m), dtype=self.ct, device=self.device)
-        be.ndfft_r2c(x, self.a, self.h2, 2)
+        if not (P > 1 and self.peer and len(self.pchunks) == 1 and len(self.rchunks) > 1):
+            be.ndfft_r2c(x, self.a, self.h2, 2)
         if P == 1:
             be.ndfft(self.a_pad, self.b_pad, self.h1, 1)        # padded lanes: 264 per row, tiles never straddle rows
             be.ndfft(self.b, out, self.h0, 0)
@@ -141,6 +148,26 @@ class SlabR2cFft3d:
             ptrs = [int(hdl.buffer_ptrs[p]) + self.rank * chunk for p in range(P)]
             recv = buf.view(n0, s1, mp)
             K = len(self.pchunks)
+            if K == 1 and len(self.rchunks) > 1:
+                main = t.cuda.current_stream(self.device)
+                self._s1.wait_stream(main)
+                self._s2.wait_stream(main)
+                for c, (r0, r1) in enumerate(self.rchunks):
+                    with t.cuda.stream(self._s1):
+                        be.ndfft_r2c(x[r0:r1], self.a[r0:r1], self.h2, 2)
+                        self._ev[c].record(self._s1)
+                    with t.cuda.stream(self._s2):
+                        self._s2.wait_event(self._ev[c])
+                        if self.scatter_smem:
+                            be.lib.dll.ndfb_hint_next_launch_smem(self.scatter_smem)
+                        be.ndfft_scatter_out(self.a_pad[r0:r1], self.h1, 1, out_shape=(r1 - r0, n1, mp),
+                                             out_strides=(s1 * mp, mp, 1), out_block=s1,
+                                             block_ptrs=[q + r0 * s1 * mp * esz for q in ptrs])
+                with t.cuda.stream(self._s2):
+                    hdl.barrier()
+                main.wait_stream(self._s2)
+                be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
+                return out
             if K == 1:
                 be.ndfft_scatter_out(self.a_pad, self.h1, 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1),
                                      out_block=s1, block_ptrs=ptrs)

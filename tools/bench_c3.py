@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--peer", default="auto", help="auto | on | off: fused peer-store all-to-all vs NCCL all_to_all_single")
     ap.add_argument("--chunks", type=int, default=1)
+    ap.add_argument("--row-chunks", type=int, default=1)
+    ap.add_argument("--scatter-smem", type=int, default=-1, help="shared-memory floor (bytes) of the scatter launch; -1 = auto")
     ap.add_argument("--graph", action="store_true", help="replay the forward transform from a CUDA graph (removes host launch overhead)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -34,7 +36,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from ndrustfft_b200.dist import SlabR2cFft3d
     n = a.n
-    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=a.chunks, peer={'auto': 'auto', 'on': True, 'off': False}[a.peer])
+    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=a.chunks, peer={'auto': 'auto', 'on': True, 'off': False}[a.peer],
+                        row_chunks=a.row_chunks, scatter_smem=None if a.scatter_smem < 0 else a.scatter_smem)
     g = torch.Generator(device=dev); g.manual_seed(0xB200 + 48 + rank)
     x = torch.rand((n // world, n, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
     out = torch.empty((n, n // world, n // 2 + 1), dtype=torch.complex128, device=dev)
@@ -79,7 +82,7 @@ def main():
         peak = 6650.0
     if rank == 0:
         line = {"cfg": "c3", "call": f"rfft3d {n}^3 f64 slab x{world}", "n_gpus": world, "ms": ms, "GFLOP/s": flops / (ms * 1e-3) / 1e9,
-                "hbm_frac_per_gpu": nbytes / world / (ms * 1e-3) / 1e9 / peak, "roundtrip_rel_l2": rel, "cuda_graph": bool(a.graph), "chunks": a.chunks, "exchange": ("peer stores fused into the axis-1 kernel" if plan.peer else ("NCCL all_to_all_single" if world > 1 else "none")),
+                "hbm_frac_per_gpu": nbytes / world / (ms * 1e-3) / 1e9 / peak, "roundtrip_rel_l2": rel, "cuda_graph": bool(a.graph), "chunks": a.chunks, "row_chunks": a.row_chunks, "scatter_smem": getattr(plan, "scatter_smem", None), "exchange": ("peer stores fused into the axis-1 kernel" if plan.peer else ("NCCL all_to_all_single" if world > 1 else "none")),
                 "a2a_bytes_sent_per_rank": plan.bytes_sent_per_rank(),
                 "nvlink_time_at_770GBs_ms": plan.bytes_sent_per_rank() / 770e9 * 1e3 if world > 1 else 0.0}
         print(json.dumps(line))
