@@ -142,7 +142,7 @@ static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
 // ------------------------------------------------------------------------------------------------------
 struct Pool {
     struct Slot { void* p = nullptr; size_t bytes = 0; int device = -1; };
-    Slot slots[5];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows
+    Slot slots[7];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows, 5: nested four-step workspace
     ~Pool() {}  // device memory is reclaimed at process exit; explicit release via ndfb_release_workspaces
     int get(int which, int device, size_t bytes, void** out) {
         Slot& s = slots[which];
@@ -542,11 +542,16 @@ static bool fits_one_tile(ndfb_plan* p, const CoreTables& t, size_t cs) {
 // C2C of a length too long for one CTA's shared memory: four-step N = N1*N2 through a device workspace.
 template <typename R>
 static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale, const void* in, void* out,
-                          std::vector<BDim> dims, long long is_axis, long long os_axis, stream_t stream) {
+                          std::vector<BDim> dims, long long is_axis, long long os_axis, stream_t stream,
+                          int depth = 0, int conj_in_override = -1) {
+    // conj_in_override: nested calls transform the workspace (already conjugated by the outer pass 1) and only need the
+    // output conjugation + scale of an inverse transform
+    const bool conj_in = conj_in_override >= 0 ? conj_in_override != 0 : inverse;
     const size_t cs = sizeof(Cx<R>);
     const size_t cap = dev_smem_cap(p->device) - 1024;
-    const long long cap1 = (long long)((cap - 256) / (4 * cs));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
-    const long long cap2 = (long long)((cap - 256) / cs);
+    long long cap1 = (long long)((cap - 256) / (4 * cs));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
+    long long cap2 = (long long)((cap - 256) / cs);
+    if (const char* f = std::getenv("NDFB_FS_CAP")) cap1 = cap2 = atoll(f);   // test hook: pretend the chip is tiny
     if (!is_smooth(N)) return fail(NDFB_E_UNSUPPORTED, "length %lld has a prime factor > 13 and is too long for the single-pass Bluestein kernel", N);
     // N1 * N2 = N with both factors on chip; prefer factors that have an instantiated Stockham schedule (and, for the
     // column pass, a tile at least one 32-byte sector wide), then the most square split
@@ -559,11 +564,23 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
         long long cands[2] = {d, N / d};
         for (long long n1 : cands) {
             long long n2 = N / n1;
-            if (n1 > cap1 || n2 > cap2 || n1 < 2 || n2 < 2) continue;
-            int score = 0;
+            const bool nested = n2 > cap2;
+            if (n1 > cap1 || n1 < 2 || n2 < 2) continue;
+            if (nested && (depth > 0 || strided_lanes || n2 > cap1 * cap2 || (int)dims.size() + 2 > kMaxBatchDims)) continue;
+            if (const char* f = std::getenv("NDFB_FS_N1")) { if (depth == 0 && atoll(f) != n1) continue; }
+            else if (nested && n1 != 256) continue;    // three-pass split: 256-point first pass (256-byte rows in f32)
+            int score = nested ? 1 : 0;
+            if (nested) {
+                const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
+                if (e1 && (size_t)e1->L * cs >= 128) score += 3;
+                // a two-pass split whose column pass has full 64-byte rows is still better than three passes
+                if (score > best_score) { best_score = score; best1 = n1; }
+                continue;
+            }
             const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
             const SfftEntry* e2 = find_sfft(sizeof(R) == 8, (int)n2, strided_lanes, 1 << 20);
             if (e1 && (size_t)e1->L * cs >= 32) score += 2;
+            if (e1 && (size_t)e1->L * cs >= 64) score += 1;
             if (e2 && (!strided_lanes || (size_t)e2->L * cs >= 32)) score += 2;
             if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
@@ -574,12 +591,13 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     long long nb = 1;
     for (auto& d : dims) nb *= d.size;
     void* ws = nullptr;
-    int rc = g_pool.get(2, p->device, (size_t)nb * (size_t)N * cs, &ws);
+    int rc = g_pool.get(depth == 0 ? 2 : 5, p->device, (size_t)nb * (size_t)N * cs, &ws);
     if (rc) return rc;
+    const bool nested2 = N2 > cap2;
     Core* c1 = get_core(p, TK_C2C, (int)N1);
-    Core* c2 = get_core(p, TK_C2C, (int)N2);
+    Core* c2 = nested2 ? nullptr : get_core(p, TK_C2C, (int)N2);
     if ((rc = ensure_device<R>(p, c1))) return rc;
-    if ((rc = ensure_device<R>(p, c2))) return rc;
+    if (c2 && (rc = ensure_device<R>(p, c2))) return rc;
     ndfb_plan::FsTw fs;
     if ((rc = get_fs_twiddles<R>(p, N, &fs))) return rc;
     const bool strided = strided_lanes;
@@ -614,13 +632,15 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
         for (size_t d = 1; d < dims.size(); ++d) { s2.dims.push_back({dims[d].size, wstride, dims[d].os}); wstride *= dims[d].size; }
         s2.is_axis = W0; s2.os_axis = N1 * os_axis;
     }
-    s1.conj_in = inverse; s1.fs_twiddle = 1; s1.fs = fs;
+    s1.conj_in = conj_in; s1.fs_twiddle = 1; s1.fs = fs;
     if ((rc = launch_c2c<R>(p, s1, stream))) return rc;
     s2.conj_out = inverse; s2.scale = scale;
     {
         const bool trace = std::getenv("NDFB_TRACE") != nullptr;
-        if (trace) fprintf(stderr, "[ndfb] four-step N=%lld = %lld x %lld (%s lanes)\n", N, N1, N2, strided ? "strided" : "contiguous");
+        if (trace) fprintf(stderr, "[ndfb] four-step N=%lld = %lld x %lld (%s lanes%s)\n", N, N1, N2, strided ? "strided" : "contiguous", nested2 ? ", second factor split again" : "");
     }
+    if (nested2)   // the second factor is itself too long for one CTA: split it again (three passes in total)
+        return exec_four_step<R>(p, N2, inverse, scale, s2.in, s2.out, s2.dims, s2.is_axis, s2.os_axis, stream, depth + 1, /*conj_in=*/0);
     return launch_c2c<R>(p, s2, stream);
 }
 

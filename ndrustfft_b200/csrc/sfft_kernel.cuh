@@ -331,10 +331,16 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
     constexpr int RPITCH = 2 * S::NPAD;
     auto sreal = [&](int t) -> R& { return smem_r[c.l * RPITCH + t]; };
     auto gin = [&](int t) -> R { return valid ? in_r[(long long)t * is_axis] : zero; };          // real input element t
-    auto xin = [&](int t) -> R { return STAGE_IN ? sreal(t) : gin(t); };
 
+    // staged complex slot j of this lane (two adjacent reals)
+    auto scx = [&](int j) -> Cx<R>& { return reinterpret_cast<Cx<R>*>(smem_r + c.l * RPITCH)[j]; };
     if (STAGE_IN) {
-        for (int t = c.i; t < n; t += S::TL) sreal(t) = gin(t);
+        // coalesced global read; the kind's reorder is applied on the shared-memory side so that the first pass reads
+        // plain complex slots (conflict free):  DCT-II: Makhoul order v[p(t)];  DCT-IV: u[j] = (x[2j], x[n-1-2j])
+        for (int t = c.i; t < n; t += S::TL) {
+            const int pos = KIND == RK_DCT2 ? ((t & 1) ? n - 1 - (t >> 1) : (t >> 1)) : ((t & 1) ? n - t : t);
+            sreal(pos) = gin(t);
+        }
         __syncthreads();
     }
 
@@ -368,10 +374,12 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
             return cmake<R>(gin(t0 <= N ? t0 : 2 * N - t0), gin(t1 <= N ? t1 : 2 * N - t1));
         } else if (KIND == RK_DCT2) {
             // Makhoul: v[t] = x[2t] (t < N) else x[2(n-1-t)+1]; z[j] = (v[2j], v[2j+1])
+            if (STAGE_IN) return scx(j);
             const int t0 = 2 * j, t1 = 2 * j + 1;
-            return cmake<R>(xin(t0 < N ? 2 * t0 : 2 * (n - 1 - t0) + 1), xin(t1 < N ? 2 * t1 : 2 * (n - 1 - t1) + 1));
+            return cmake<R>(gin(t0 < N ? 2 * t0 : 2 * (n - 1 - t0) + 1), gin(t1 < N ? 2 * t1 : 2 * (n - 1 - t1) + 1));
         } else {  // RK_DCT4
-            return cmul(cmake<R>(xin(2 * j), xin(n - 1 - 2 * j)), ldg(&tabA[j]));
+            if (STAGE_IN) return cmul(scx(j), ldg(&tabA[j]));
+            return cmul(cmake<R>(gin(2 * j), gin(n - 1 - 2 * j)), ldg(&tabA[j]));
         }
     };
 
@@ -394,10 +402,12 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
             // v[2k] = y.x, v[2k+1] = -y.y;  x[o(t)] = v[t]/2, o(t) = 2t (t < N) else 2(n-1-t)+1
             const int t0 = 2 * k, t1 = 2 * k + 1;
             const R h = (R)0.5 * sc;
+            if (STAGE_OUT) { scx(k) = cmake<R>(h * y.x, -h * y.y); return; }   // reorder applied by the copy-out loop
             put(t0 < N ? 2 * t0 : 2 * (n - 1 - t0) + 1, h * y.x);
             put(t1 < N ? 2 * t1 : 2 * (n - 1 - t1) + 1, -h * y.y);
         } else {  // RK_DCT4
             const Cx<R> C = cmul(y, ldg(&tabB[k]));
+            if (STAGE_OUT) { scx(k) = cmake<R>(sc * C.x, -sc * C.y); return; }
             put(2 * k, sc * C.x);
             put(n - 1 - 2 * k, -sc * C.y);
         }
@@ -430,7 +440,11 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
     if (STAGE_OUT) {
         __syncthreads();
         if (valid)
-            for (int t = c.i; t < n; t += S::TL) out_r[(long long)t * os_axis] = sreal(t);
+            for (int t = c.i; t < n; t += S::TL) {
+                // DCT-III: out[t] = v[p(t)] (inverse Makhoul);  DCT-IV: even t from the real parts, odd t from the imaginary ones
+                const int pos = KIND == RK_DCT3 ? ((t & 1) ? n - 1 - (t >> 1) : (t >> 1)) : ((t & 1) ? n - t : t);
+                out_r[(long long)t * os_axis] = sreal(pos);
+            }
     }
 }
 

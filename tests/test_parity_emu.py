@@ -350,3 +350,17 @@ def test_staged_path_prime_c2c(hs):
         hs.run("ndfft", 97, (4, 97, 2), 1, np.float32, seed=3)
     finally:
         del os.environ["NDFB_FORCE_STAGED"]
+
+
+def test_three_pass_decomposition(hs, capfd):
+    """Rows too long for two on-chip factors split the second factor again (2^24 = 256 x (256 x 256) on the GPU);
+    NDFB_FS_CAP shrinks the 'chip' so the emulator can run the same code at 16384 = 16 x (32 x 32)."""
+    import os
+    os.environ.update({"NDFB_FORCE_FOUR_STEP": "1", "NDFB_FS_CAP": "64", "NDFB_FS_N1": "16", "NDFB_TRACE": "1"})
+    try:
+        hs.run("ndfft", 16384, (2, 16384), 1, np.float32, seed=1)
+        hs.run("ndifft", 16384, (1, 16384), 1, np.float64, seed=2)
+    finally:
+        for k in ("NDFB_FORCE_FOUR_STEP", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_TRACE"):
+            del os.environ[k]
+    assert capfd.readouterr().err.count("second factor split again") == 2
