@@ -572,8 +572,9 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             int score = nested ? 1 : 0;
             if (nested) {
                 const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
-                if (e1 && (size_t)e1->L * cs >= 128) score += 3;
-                // a two-pass split whose column pass has full 64-byte rows is still better than three passes
+                if (e1 && (size_t)e1->L * cs >= 128) score += 2;
+                // measured on B200 (2^24 f32 x 64): 256 x (256 x 256) 22.8 ms vs 2048 x 8192 15.1 ms, so any two-pass split with
+                // instantiated schedules outranks the three-pass one; it remains the fallback for lengths beyond two factors
                 if (score > best_score) { best_score = score; best1 = n1; }
                 continue;
             }
