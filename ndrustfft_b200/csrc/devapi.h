@@ -38,6 +38,7 @@ size_t& launch_smem_floor();               // thread-local, consumed by the next
 #ifdef NDFB_EMU
 typedef void* stream_t;
 inline int dev_set(int) { return 0; }
+struct DeviceGuard {};
 inline int dev_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : NDFB_E_ALLOC; }
 inline void dev_free(void* p) { std::free(p); }
 inline int dev_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memcpy(d, h, bytes); return 0; }
@@ -64,6 +65,12 @@ inline int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
     } while (0)
 inline int dev_set(int dev) { NDFB_CUDA(cudaSetDevice(dev)); return 0; }
+// restores the caller's current device when an entry point returns (the host application, e.g. torch, owns it)
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 inline int dev_malloc(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(NDFB_E_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
@@ -85,8 +92,10 @@ inline int dev_sm_count(int dev) {
 }
 template <typename K, typename A>
 inline int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stream_t s, const A& a) {
-    static thread_local std::map<const void*, size_t> attr_set;
-    const void* key = (const void*)kernel;
+    static thread_local std::map<std::pair<int, const void*>, size_t> attr_set;   // per (device, kernel)
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    const std::pair<int, const void*> key(cur_dev, (const void*)kernel);
     auto it = attr_set.find(key);
     if (it == attr_set.end() || it->second < smem) {
         NDFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));

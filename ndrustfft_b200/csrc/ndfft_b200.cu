@@ -1159,6 +1159,8 @@ static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_sca
     if (norm != NDFB_NORM_NONE && norm != NDFB_NORM_DEFAULT) return fail(NDFB_E_INVALID, "unknown norm %d", norm);
     if (mem != NDFB_MEM_HOST && mem != NDFB_MEM_DEVICE) return fail(NDFB_E_INVALID, "unknown mem %d", mem);
     ndfb_plan* p = const_cast<ndfb_plan*>(plan);  // lazily built caches are guarded by mutexes
+    DeviceGuard device_guard;
+    (void)device_guard;
     OpInfo o;
     int rc = op_info(p, op, norm, &o);
     if (rc) return rc;

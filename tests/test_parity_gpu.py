@@ -376,3 +376,42 @@ def test_plan_families_reported(dev):
     assert fam(be.FftHandler(1000003, np.float32))[0] == "staged"
     assert fam(be.R2cFftHandler(1 << 20))[0] == "staged"
     assert fam(be.FftHandler(1009))[0] == "bluestein"
+
+
+def test_shared_handler_from_threads(dev):
+    """One handler used concurrently from several host threads (the reference shares `&handler` across rayon workers,
+    src/lib.rs:169-238); every thread gets its own workspaces, results must match the single-threaded ones."""
+    import threading
+    be = dev.be
+    n = 2048
+    h = be.FftHandler(n, np.float32)
+    xs = [_rand((256, n), np.float32, True, 100 + i) for i in range(4)]
+    want = []
+    for x in xs:
+        y = torch.empty_like(x); be.ndfft(x, y, h, 1); want.append(y)
+    outs = [torch.empty_like(x) for x in xs]
+    errs = []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    be.ndfft(xs[i], outs[i], h, 1)
+            s.synchronize()
+        except Exception as e:          # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errs
+    torch.cuda.synchronize()
+    for a, b in zip(outs, want):
+        assert torch.equal(a, b)
+
+
+def test_current_device_is_restored(dev):
+    be = dev.be
+    before = torch.cuda.current_device()
+    dev.run("ndfft", 64, (4, 64), 1)
+    assert torch.cuda.current_device() == before
