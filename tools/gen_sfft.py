@@ -115,7 +115,9 @@ def c2c_cols(f64):
                 if L * cs > (256 if N <= 256 else 128):   # short columns: 256-byte rows keep enough loads in flight per CTA
                     continue
                 e = make(f64, N, TL, rad, L, 1, fam)
-                if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
+                # family B keeps <= 64 registers, so a 1024-thread CTA (32 warps on a tile that owns the whole SM) is allowed
+                tmax = 1024 if (fam == 1 and e["E"] * (4 if f64 else 2) <= 32) else 512
+                if e["T"] > tmax or e["T"] < 32 or e["smem"] > 200 * 1024:
                     continue
                 cand.append(e)
             out.extend(cand[:3])  # the three widest tiles that fit
@@ -145,7 +147,8 @@ def real_entries(f64):
                 if L * rs > 128:
                     continue
                 e = make(f64, N, TL, rad, L, 1, fam, always_smem=True)
-                if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
+                tmax = 1024 if (fam == 1 and e["E"] * (4 if f64 else 2) <= 32) else 512
+                if e["T"] > tmax or e["T"] < 32 or e["smem"] > 200 * 1024:
                     continue
                 out.append(e)
                 nfit += 1
