@@ -12,7 +12,9 @@
 
 namespace ndfb {
 
-enum BigKind : int { BK_C2C = 100 };  // plus the RKind values of rsfft_kernel
+// BK_C2C, the RKind values of rsfft_kernel (even lengths, packed half-length core), and the odd-length real kinds, which run
+// a full-length complex core (DCT-IV: zero-padded 2n-point core) exactly like tile_kernel.cuh does
+enum BigKind : int { BK_C2C = 100, BK_R2C_ODD = 201, BK_C2R_ODD = 202, BK_DCT2_ODD = 203, BK_DCT3_ODD = 204, BK_DCT4_ODD = 205 };
 
 struct BigArgs {
     const void* in;       // prologue: user input;        epilogue: unused
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) big_pro_kernel(const __grid_constant__ Bi
         Cx<R> z = cmake<R>(zero, zero);
         if (j < N) {
             const LaneBase lb = lane_base(a, a.lane0 + lane, true);
-            const R* __restrict__ in_r = reinterpret_cast<const R*>(a.in) + (a.kind == RK_C2R || a.kind == BK_C2C ? 2 * lb.bi : lb.bi);
+            const R* __restrict__ in_r = reinterpret_cast<const R*>(a.in) + lb.bi;   // (only read by the real-input kinds)
             const Cx<R>* __restrict__ in_c = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
             auto gin = [&](int t) -> R { return in_r[(long long)t * a.is_axis]; };
             switch (a.kind) {
@@ -88,6 +90,23 @@ __global__ void __launch_bounds__(256) big_pro_kernel(const __grid_constant__ Bi
                     z = cmake<R>(gin(t0 < N ? 2 * t0 : 2 * (n - 1 - t0) + 1), gin(t1 < N ? 2 * t1 : 2 * (n - 1 - t1) + 1));
                 } break;
                 case RK_DCT4: z = cmul(cmake<R>(gin(2 * j), gin(n - 1 - 2 * j)), ldg(&tabA[j])); break;
+                case BK_R2C_ODD: z = cmake<R>(gin(j), zero); break;
+                case BK_C2R_ODD: {   // conj of the Hermitian completion of the half spectrum (m = n/2 + 1 bins given)
+                    const int m = n / 2 + 1;
+                    if (j < m) { z = in_c[(long long)j * a.is_axis]; if (j == 0) z.y = zero; z.y = -z.y; }
+                    else z = in_c[(long long)(n - j) * a.is_axis];
+                } break;
+                case BK_DCT2_ODD: {
+                    const int h = (n + 1) / 2;
+                    z = cmake<R>(gin(j < h ? 2 * j : 2 * (n - 1 - j) + 1), zero);
+                } break;
+                case BK_DCT3_ODD: {
+                    const Cx<R> pk = cmake<R>(gin(j), j == 0 ? zero : -gin(n - j));
+                    z = cconj(cmul(pk, cconj(ldg(&tabB[j]))));
+                } break;
+                case BK_DCT4_ODD: {
+                    if (j < n) { const Cx<R> w = ldg(&tabA[j]); const R x = gin(j); z = cmake<R>(x * w.x, x * w.y); }
+                } break;
                 default: break;
             }
             if (a.M) z = cmul(z, ldg(&chirp[j]));
@@ -119,7 +138,7 @@ __global__ void __launch_bounds__(256) big_epi_kernel(const __grid_constant__ Bi
             return cmake<R>((R)0.5 * (s.x + d.y), (R)0.5 * (s.y - d.x));
         };
         const LaneBase lb = lane_base(a, a.lane0 + lane, true);
-        R* __restrict__ out_r = reinterpret_cast<R*>(a.out) + (a.kind == RK_R2C || a.kind == BK_C2C ? 2 * lb.bo : lb.bo);
+        R* __restrict__ out_r = reinterpret_cast<R*>(a.out) + lb.bo;             // (only written by the real-output kinds)
         Cx<R>* __restrict__ out_c = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
         const long long g = (long long)k * a.os_axis;
         switch (a.kind) {
@@ -149,6 +168,14 @@ __global__ void __launch_bounds__(256) big_epi_kernel(const __grid_constant__ Bi
                 const Cx<R> C = cmul(Z(j), ldg(&tabB[j]));
                 out_r[g] = sc * ((k & 1) ? -C.y : C.x);
             } break;
+            case BK_R2C_ODD: out_c[g] = cscale(Z(k), sc); break;
+            case BK_C2R_ODD: out_r[g] = sc * Z(k).x; break;
+            case BK_DCT2_ODD: out_r[g] = sc * cmul(Z(k), ldg(&tabB[k])).x; break;
+            case BK_DCT3_ODD: {
+                const int vi = (k & 1) ? (n - 1 - (k >> 1)) : (k >> 1);
+                out_r[g] = sc * (R)0.5 * Z(vi).x;
+            } break;
+            case BK_DCT4_ODD: out_r[g] = sc * cmul(Z(k), ldg(&tabB[k])).x; break;
             default: break;
         }
     }

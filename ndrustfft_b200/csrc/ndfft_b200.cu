@@ -789,10 +789,18 @@ template <typename R>
 static int exec_big(ndfb_plan* p, const OpInfo& o, double scale, const void* in, void* out, std::vector<BDim> dims,
                     long long is_axis, long long os_axis, stream_t stream) {
     const size_t cs = sizeof(Cx<R>);
-    const int bk = o.tk == TK_C2C ? (int)BK_C2C : rkind_of(o.tk);
-    if (bk < 0) return fail(NDFB_E_UNSUPPORTED, "%s of odd length %zu does not fit one CTA's shared memory; the staged path covers complex and even-length real transforms", o.what, p->n);
+    int bk = o.tk == TK_C2C ? (int)BK_C2C : rkind_of(o.tk);
     const long long n = (long long)p->n;
-    const long long N = o.tk == TK_C2C ? n : (o.tk == TK_DCT1 ? n - 1 : n / 2);
+    long long N = o.tk == TK_C2C ? n : (o.tk == TK_DCT1 ? n - 1 : n / 2);
+    switch (o.tk) {   // odd lengths: full-length complex core
+        case TK_R2C_ODD: bk = BK_R2C_ODD; N = n; break;
+        case TK_C2R_ODD: bk = BK_C2R_ODD; N = n; break;
+        case TK_DCT2_ODD: bk = BK_DCT2_ODD; N = n; break;
+        case TK_DCT3_ODD: bk = BK_DCT3_ODD; N = n; break;
+        case TK_DCT4_ODD: bk = BK_DCT4_ODD; N = 2 * n; break;
+        default: break;
+    }
+    if (bk < 0) return fail(NDFB_E_UNSUPPORTED, "%s of length %zu has no staged schedule", o.what, p->n);
     if (N < 1) return fail(NDFB_E_UNSUPPORTED, "length too short for the staged path");
     normalize_dims(dims);
     if ((int)dims.size() > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "staged transform with more than %d batch dims", kMaxBatchDims);
@@ -917,7 +925,7 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         if (!fits_one_tile(p, c->t, cs)) single = false;
     }
     if (!single && o.os_blk) return fail(NDFB_E_UNSUPPORTED, "split output axis is only available for single-pass complex transforms");
-    if (single && !o.os_blk && std::getenv("NDFB_FORCE_STAGED") && (o.tk == TK_C2C || rkind_of(o.tk) >= 0) && p->n >= 4) single = false;
+    if (single && !o.os_blk && std::getenv("NDFB_FORCE_STAGED") && p->n >= 3) single = false;
     if (!single) {
         if (o.tk == TK_C2C && is_smooth((long long)p->n) && !std::getenv("NDFB_FORCE_STAGED"))
             return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, in, out, dims, is_axis, os_axis, stream);
@@ -1218,7 +1226,7 @@ size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {
         if (o.tk == TK_DCT1) N_est = (long long)p->n - 1;
         if (p->n == 0 || (o.tk == TK_DCT1 && p->n < 2)) { s += ",\"family\":\"empty\"}"; continue; }
         if ((size_t)N_est * cs + 64 > 226 * 1024) {
-            const bool staged_ok = o.tk == TK_C2C || rkind_of(o.tk) >= 0;
+            const bool staged_ok = true;   // every kind has a staged schedule (big_kernels.cuh)
             s += std::string(",\"family\":\"") + (o.tk == TK_C2C && is_smooth((long long)p->n) ? "four-step" : (staged_ok ? "staged" : "unsupported")) + "\",\"N\":" + std::to_string(N_est) + "}";
             continue;
         }

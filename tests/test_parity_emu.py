@@ -325,7 +325,7 @@ def test_scatter_output_blocks(hs):
 
 # ---- staged path (big_kernels.cuh): prologue kernel -> complex core on workspace rows -> epilogue kernel ----
 @pytest.mark.parametrize("op", ["ndfft", "ndifft", "ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4"])
-@pytest.mark.parametrize("n", [64, 90, 202, 1018])     # smooth, smooth, 2*101 (Bluestein core), 2*509
+@pytest.mark.parametrize("n", [64, 90, 202, 1018, 45, 101, 1009])     # even: smooth, smooth, 2*101 (Bluestein core), 2*509; odd: smooth, prime, prime
 def test_staged_path(hs, op, n, capfd):
     """Lengths that overflow one CTA's shared memory take the staged route; NDFB_FORCE_STAGED runs it at test sizes."""
     import os

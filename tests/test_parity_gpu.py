@@ -361,7 +361,10 @@ def test_config5b_2pow24_c64_batch64(dev):
                                       ("nddct2", 1 << 16, np.float64), ("nddct3", 1 << 16, np.float64),
                                       ("nddct4", 40000, np.float32), ("nddct1", 32769, np.float64),
                                       ("ndfft", 65537, np.float64), ("ndifft", 1000003, np.float32),
-                                      ("ndfft_r2c", 2 * 10007, np.float64)])
+                                      ("ndfft_r2c", 2 * 10007, np.float64),
+                                      # odd lengths beyond one CTA: full-length complex core on workspace rows
+                                      ("ndfft_r2c", 30011, np.float64), ("ndifft_r2c", 20001, np.float64),
+                                      ("nddct2", 20001, np.float64), ("nddct3", 16385, np.float32), ("nddct4", 15001, np.float32)])
 def test_staged_long_lanes(dev, op, n, rd):
     dev.run(op, n, (3, n), 1, rd, seed=n % 977)
     if n <= (1 << 16):
