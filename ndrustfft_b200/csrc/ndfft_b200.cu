@@ -401,6 +401,23 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     return e->launch(a, (unsigned)grid, stream);
 }
 
+template <typename R>
+static int get_big_bluestein(ndfb_plan* p, long long N, ndfb_plan::BigBlu* out);
+
+static const BsfftEntry* find_bsfft(bool f64, int M, bool cols, long long nlanes, long long axis_stride_bytes) {
+    static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
+    if (disabled || std::getenv("NDFB_DISABLE_BSFFT")) return nullptr;
+    const BsfftEntry* tab = f64 ? kBsfft_f64 : kBsfft_f32;
+    const int count = f64 ? kBsfft_f64_count : kBsfft_f32_count;
+    const BsfftEntry* best = nullptr;
+    for (int i = 0; i < count; ++i) {
+        const BsfftEntry* e = &tab[i];
+        if (e->M != M || e->cols != (cols ? 1 : 0)) continue;
+        if (better_entry(e, best, nlanes, 1, f64 ? (size_t)16 : (size_t)8, axis_stride_bytes)) best = e;
+    }
+    return best;
+}
+
 // C2C launch: the instantiated Stockham schedule when there is one, else the general tile kernel
 template <typename R>
 static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
@@ -419,6 +436,42 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         }
     }
     if (s.nblk_ptr) return fail(NDFB_E_UNSUPPORTED, "scattered output blocks need a length with an instantiated Stockham schedule");
+    // no schedule for this length: Bluestein fused around two power-of-two Stockham transforms (bsfft_kernel), if M fits
+    if (t.kind == TK_C2C && t.N >= 2 && !s.fs_twiddle && !s.os_blk && (int)s.dims.size() <= kMaxBatchDims) {
+        long long M = 1;
+        while (M < 2LL * t.N - 1) M <<= 1;
+        long long nlanes = 1;
+        for (auto& d : s.dims) nlanes *= d.size;
+        const bool have_batch = !s.dims.empty() && nlanes > 1;
+        const bool cols = have_batch && (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
+        const BsfftEntry* e = M <= 8192 ? find_bsfft(sizeof(R) == 8, (int)M, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>)) : nullptr;
+        if (e && nlanes > 0) {
+            ndfb_plan::BigBlu blu;
+            int rc = get_big_bluestein<R>(p, t.N, &blu);
+            if (rc) return rc;
+            BsfftArgs ba;
+            std::memset(&ba, 0, sizeof ba);
+            SfftArgs& a = ba.base;
+            a.in = s.in; a.out = s.out; a.nlanes = nlanes;
+            a.nbd = (int)s.dims.size();
+            for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
+            a.is_axis = s.is_axis; a.os_axis = s.os_axis;
+            a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
+            SfftEntry proxy;
+            std::memset(&proxy, 0, sizeof proxy);
+            for (int i = 0; i < 4; ++i) proxy.r[i] = e->r[i];
+            proxy.twtotal = e->twtotal;
+            void* twd = nullptr;
+            if ((rc = get_sfft_twiddles<R>(p, s.core, &proxy, &twd))) return rc;
+            a.tw = twd;
+            ba.n = t.N; ba.chirp = blu.chirp; ba.bhat = blu.bhat;
+            const bool trace = std::getenv("NDFB_TRACE") != nullptr;
+            if (trace) fprintf(stderr, "[ndfb] bsfft %s N=%d M=%d %s L=%d T=%d smem=%zu lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", t.N, e->M, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
+            const long long grid = (nlanes + e->L - 1) / e->L;
+            if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+            return e->launch(ba, (unsigned)grid, stream);
+        }
+    }
     return launch_tile<R>(p, s, stream);
 }
 

@@ -271,6 +271,64 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Bluestein (chirp-z) C2C for lengths without an instantiated schedule, fused in ONE kernel around two Stockham
+// transforms of a power-of-two length M >= 2N-1 that does have one:
+//     a[j] = x[j] c[j] (zero padded to M)  ->  A = FFT_M(a)  ->  conj(A * bhat)  ->  FFT_M  ->  X[k] = conj(.) c[k]
+// The tile never leaves the chip between the two transforms (the first one stores into the shared buffer, the second
+// loads from it), so HBM traffic stays input-once + output-once.  Replaces rustfft's BluesteinsAlgorithm / RadersAlgorithm
+// behind plan_fft_forward/inverse (src/lib.rs:295-297).
+// ------------------------------------------------------------------------------------------------------
+struct BsfftArgs {
+    SfftArgs base;       // lanes, strides, conj flags, scale, per-pass twiddles of the M-point schedule
+    int n;               // actual transform length N (<= (M+1)/2)
+    const void* chirp;   // c[j] = exp(-i pi j^2 / N), j < N
+    const void* bhat;    // FFT_M(conj-chirp kernel) / M, natural order
+};
+
+template <typename R, class S, int L, bool COLS, int MINB>
+__global__ void __launch_bounds__(S::TL* L, MINB) bsfft_kernel(const __grid_constant__ BsfftArgs ba) {
+    const SfftArgs& a = ba.base;
+    NDFB_DYN_SMEM(smem_raw);
+    SfftCtx<R, S, L, COLS> c;
+    c.smem = reinterpret_cast<Cx<R>*>(smem_raw);
+    const int tid = threadIdx.x;
+    if (COLS) { c.l = tid % L; c.i = tid / L; }
+    else { c.i = tid % S::TL; c.l = tid / S::TL; }
+    const long long g = (long long)blockIdx.x * L + c.l;
+    c.valid = g < a.nlanes;
+    const bool valid = c.valid;
+    const LaneBase lb = lane_base(a, g, valid, 0);
+    const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
+    Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
+    const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
+    const Cx<R>* __restrict__ chirp = reinterpret_cast<const Cx<R>*>(ba.chirp);
+    const Cx<R>* __restrict__ bhat = reinterpret_cast<const Cx<R>*>(ba.bhat);
+    const long long is_axis = a.is_axis, os_axis = a.os_axis;
+    const int N = ba.n;
+    const R sc = (R)a.scale;
+    const R sy = a.conj_out ? -sc : sc;
+    const R sgn_in = a.conj_in ? (R)-1 : (R)1;
+    const R zero = (R)0;
+    Cx<R> v[S::E];
+    auto load1 = [&](int j) -> Cx<R> {
+        if (j >= N || !valid) return cmake<R>(zero, zero);
+        Cx<R> x = in[(long long)j * is_axis];
+        x.y *= sgn_in;
+        return cmul(x, ldg(&chirp[j]));
+    };
+    auto store1 = [&](int k, Cx<R> val) { c.smem[c.addr(k)] = cconj(cmul(val, ldg(&bhat[k]))); };
+    SfftAll<R, S, L, COLS, 0, false, (S::NP > 1)>::run(c, v, tw, load1, store1);
+    __syncthreads();
+    auto load2 = [&](int j) -> Cx<R> { return c.smem[c.addr(j)]; };
+    auto store2 = [&](int k, Cx<R> val) {
+        if (k >= N || !valid) return;
+        const Cx<R> y = cmul(cconj(val), ldg(&chirp[k]));
+        out[(long long)k * os_axis] = cmake<R>(y.x * sc, y.y * sy);
+    };
+    SfftAll<R, S, L, COLS, 0, true, false>::run(c, v, tw, load2, store2);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // real transforms of even length around the same Stockham core of N = n/2 (DCT-I: N = n-1) complex points:
 // R2C, C2R, DCT-I..IV.  The algebra is the one verified in tests/kernel_math_model.py and used by
 // tile_kernel.cuh; here it is fused into the first-pass loads and the last-pass stores:

@@ -364,3 +364,34 @@ def test_three_pass_decomposition(hs, capfd):
         for k in ("NDFB_FORCE_FOUR_STEP", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_TRACE"):
             del os.environ[k]
     assert capfd.readouterr().err.count("second factor split again") == 2
+
+
+# ---- fused Bluestein on the Stockham passes (bsfft_kernel): lengths with no schedule of their own ----
+@pytest.mark.parametrize("n", [17, 31, 97, 257, 1009, 2047, 2049])
+def test_bsfft_lengths(hs, n, capfd):
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        if n <= 2048:                                    # f64: M = 4096 is the largest instantiated length
+            hs.run("ndfft", n, (3, n), 1, np.float64, seed=n)
+            hs.run("ndifft", n, (n, 5), 0, np.float64, seed=n + 1)
+        hs.run("ndifft", n, (2, n), 1, np.float32, seed=n + 2)
+        hs.run("ndfft", n, (n, 9), 0, np.float32, seed=n + 3)
+        hs.run("ndfft", n, (2, n, 3), 1, np.float32, norm="none", seed=n + 4)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    # (f64 columns at M = 4096 and f32 columns at M = 8192 have no tile that fits: those calls stay on the general kernel)
+    assert capfd.readouterr().err.count("[ndfb] bsfft") == (5 if n <= 1024 else 4 if n <= 2048 else 1)
+
+
+def test_bsfft_and_general_bluestein_agree(hs, capfd):
+    import os
+    os.environ["NDFB_DISABLE_BSFFT"] = "1"
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run("ndfft", 1009, (2, 1009), 1, np.float64, seed=5)
+        hs.run("ndfft", 97, (97, 4), 0, np.float32, seed=6)
+    finally:
+        del os.environ["NDFB_DISABLE_BSFFT"]
+        del os.environ["NDFB_TRACE"]
+    assert "[ndfb] bsfft" not in capfd.readouterr().err

@@ -157,6 +157,30 @@ def real_entries(f64):
     return dedup(out)
 
 
+def bluestein_entries(f64):
+    """Fused Bluestein kernels: M-point family-B schedules (rows: one tile shape, columns: the two widest that fit)."""
+    out = []
+    cs = 16 if f64 else 8
+    for M in [64, 128, 256, 512, 1024, 2048, 4096] + ([] if f64 else [8192]):
+        sc = schedule(M, f64, 1)
+        if sc is None:
+            continue
+        TL, rad = sc
+        if TL < 2 or TL > 512:
+            continue
+        out.append(make(f64, M, TL, rad, rows_L(M, TL, rad[0], cs), 0, 1, always_smem=True))
+        cand = []
+        for L in (16, 8, 4, 2):
+            if L * cs > 128:
+                continue
+            e = make(f64, M, TL, rad, L, 1, 1, always_smem=True)
+            if e["T"] > 512 or e["T"] < 32 or e["smem"] > 200 * 1024:
+                continue
+            cand.append(e)
+        out.extend(cand[:2])
+    return dedup(out)
+
+
 def dedup(entries):
     seen, out = set(), []
     for e in entries:
@@ -182,7 +206,7 @@ def write(path, lines):
 
 def main():
     for f in os.listdir(OUT):
-        if f.startswith(("sfft_inst_", "rsfft_inst_")) and f.endswith(".cu"):
+        if f.startswith(("sfft_inst_", "rsfft_inst_", "bsfft_inst_")) and f.endswith(".cu"):
             os.remove(os.path.join(OUT, f))
     total = 0
     head = ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "sfft_inst.h"', "", "namespace ndfb {", ""]
@@ -190,6 +214,12 @@ def main():
     for name, ents in groups.items():
         write(f"sfft_inst_{name}.cu", head + [f"const SfftEntry kSfft_{name}[] = {{"] + [fmt(e, "SFFT_ENTRY") for e in ents] +
               ["};", f"const int kSfft_{name}_count = {len(ents)};", "", "}  // namespace ndfb"])
+        total += len(ents)
+    for f64 in (0, 1):
+        nm = "f64" if f64 else "f32"
+        ents = bluestein_entries(f64)
+        write(f"bsfft_inst_{nm}.cu", head + [f"const BsfftEntry kBsfft_{nm}[] = {{"] + [fmt(e, "BSFFT_ENTRY") for e in ents] +
+              ["};", f"const int kBsfft_{nm}_count = {len(ents)};", "", "}  // namespace ndfb"])
         total += len(ents)
     rnames = []
     for f64 in (0, 1):
