@@ -83,7 +83,10 @@ NDFB_API size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap)
 /* One nd* call.  shape/strides describe `in` and `out` as ndarray does: `ndim` extents and SIGNED strides
  * in ELEMENTS of the respective element type (real scalar, or interleaved {re,im} complex).  `mem` says
  * whether both pointers are host memory (copied through pinned staging; synchronous) or device memory on
- * the plan's device (asynchronous on `stream`, a cudaStream_t; NULL = default stream). */
+ * the plan's device (asynchronous on `stream`, a cudaStream_t; NULL = default stream).
+ * In place: `in == out` with identical shape and strides is supported for the ops that keep shape and element type
+ * (FFT, IFFT, DCT1..4) — every tile is read completely before it is written (the reference always takes a separate
+ * output, src/lib.rs:107).  Partially overlapping arrays are not supported. */
 NDFB_API int ndfb_exec(const ndfb_plan* plan, int op, int norm,
               const void* in, void* out, int ndim,
               const size_t* shape_in, const ptrdiff_t* strides_in,
@@ -123,6 +126,30 @@ NDFB_API int ndfb_exec_scatter_out(const ndfb_plan* plan, int op, int norm, doub
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
 NDFB_API const char* ndfb_last_error(void);
+
+/* One axis transform of a chain. */
+typedef struct ndfb_step {
+    const ndfb_plan* plan;   /* all plans of a chain share dtype and device */
+    int op;                  /* NDFB_OP_* valid for the plan's kind */
+    int norm;                /* NDFB_NORM_NONE / NDFB_NORM_DEFAULT */
+    int axis;
+} ndfb_step;
+
+/* Multi-axis transform: applies steps[0], steps[1], ... in order, step i reading what step i-1 wrote — the same
+ * result as nsteps ndfb_exec calls through intermediate `work` arrays, which is how the reference's users compose
+ * fft2 / rfft2 / fft3 (examples/fft2.rs:23-27 and :55-59, examples/rfft2.rs:29-33).  Here the
+ * intermediates never leave the device: they live in `out` itself when shape and element type allow (later steps then
+ * run in place) or in library workspaces, and with mem == NDFB_MEM_HOST the data crosses PCIe once in each direction
+ * (first step overlapped with the upload, last step with the download) instead of once per axis.
+ * shape_in / strides_in describe `in` (element type = input type of steps[0]); shape_out / strides_out describe `out`
+ * (output type of the last step).  The shape evolves along each r2c / c2r axis exactly as in the single calls, and the
+ * same size checks apply per step (NDFB_E_SIZE_MISMATCH carries the reference's message).  `in` is never modified;
+ * `in == out` is allowed when strides are identical and every step keeps shape and element type (C2C, DCT). */
+NDFB_API int ndfb_exec_chain(const ndfb_step* steps, int nsteps,
+                    const void* in, void* out, int ndim,
+                    const size_t* shape_in, const ptrdiff_t* strides_in,
+                    const size_t* shape_out, const ptrdiff_t* strides_out,
+                    int mem, void* stream);
 
 /* Library identification: "ndfft_b200 <version> sm_100a" for the CUDA build. */
 NDFB_API const char* ndfb_version(void);

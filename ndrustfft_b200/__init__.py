@@ -27,6 +27,7 @@ __all__ = [
     "ndfft", "ndifft", "ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4",
     "ndfft_par", "ndifft_par", "ndfft_r2c_par", "ndifft_r2c_par",
     "nddct1_par", "nddct2_par", "nddct3_par", "nddct4_par",
+    "ndchain", "fft2", "ifft2", "rfft2", "irfft2",
     "NdfftError", "SizeMismatch", "Backend",
 ]
 
@@ -279,6 +280,91 @@ class Backend:
     def nddct2(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT2, input, output, axis)
     def nddct3(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT3, input, output, axis)
     def nddct4(self, input, output, handler, axis): self._run(handler, _lib.OP_DCT4, input, output, axis)
+
+    # -- multi-axis chains (ndfb_exec_chain; the fft2 / rfft2 pattern of examples/fft2.rs:23-27, examples/rfft2.rs:29-33) --
+    _CHAIN_OPS = {"ndfft": _lib.OP_FFT, "ndifft": _lib.OP_IFFT, "ndfft_r2c": _lib.OP_R2C, "ndifft_r2c": _lib.OP_C2R,
+                  "nddct1": _lib.OP_DCT1, "nddct2": _lib.OP_DCT2, "nddct3": _lib.OP_DCT3, "nddct4": _lib.OP_DCT4}
+
+    def ndchain(self, input, output, steps):
+        """Applies `steps` = [(function name, handler, axis), ...] in order, e.g. rfft2 of the reference's example is
+        `[("ndfft_r2c", handler_ax1, 1), ("ndfft", handler_ax0, 0)]`.  Same result as the separate calls through `work`
+        arrays; the intermediates stay on the GPU and host arrays cross PCIe once each way."""
+        steps = [(str(name).removesuffix("_par"), h, int(ax)) for name, h, ax in steps]
+        if not steps:
+            raise ValueError("at least one step expected")
+        for name, _, _ in steps:
+            if name not in self._CHAIN_OPS:
+                raise ValueError(f"unknown transform {name!r}")
+        if any(h.norm.kind == "custom" for _, h, _ in steps):
+            return self._chain_stepwise(input, output, steps)
+        vi, vo = _view_of(input), _view_of(output)
+        if len(vi.shape) != len(vo.shape):
+            raise AssertionError("input and output must have the same number of dimensions")
+        ndim = len(vi.shape)
+        if ndim < 1:
+            raise IndexError("0-dimensional arrays have no axis")
+        first, last = self._CHAIN_OPS[steps[0][0]], self._CHAIN_OPS[steps[-1][0]]
+        rd = steps[0][1].dtype
+        cd = np.dtype(np.complex64 if rd == np.float32 else np.complex128)
+        want_in = cd if first in (_lib.OP_FFT, _lib.OP_IFFT, _lib.OP_C2R) else rd
+        want_out = cd if last in (_lib.OP_FFT, _lib.OP_IFFT, _lib.OP_R2C) else rd
+        if vi.dtype != want_in or vo.dtype != want_out:
+            raise TypeError(f"element types do not match the handlers: got {vi.dtype} -> {vo.dtype}, expected {want_in} -> {want_out}")
+        if (vi.device is None) != (vo.device is None):
+            raise ValueError("input and output must both be host arrays or both be device tensors")
+        if vi.device is not None and any(vi.device != h.device or vo.device != h.device for _, h, _ in steps):
+            raise ValueError("tensors must live on the handlers' device")
+        arr = (_lib.Step * len(steps))()
+        for i, (name, h, ax) in enumerate(steps):
+            arr[i].plan, arr[i].op, arr[i].axis = h._plan.value if hasattr(h._plan, "value") else h._plan, self._CHAIN_OPS[name], ax
+            arr[i].norm = _lib.NORM_DEFAULT if h.norm.kind == "default" else _lib.NORM_NONE
+        SZ = ctypes.c_size_t * ndim
+        PD = ctypes.c_ssize_t * ndim
+        mem = _lib.MEM_HOST if vi.device is None else _lib.MEM_DEVICE
+        rc = self.lib.dll.ndfb_exec_chain(arr, len(steps), ctypes.c_void_p(vi.ptr), ctypes.c_void_p(vo.ptr), ndim,
+                                          SZ(*vi.shape), PD(*vi.strides), SZ(*vo.shape), PD(*vo.strides), mem,
+                                          ctypes.c_void_p(vi.stream or 0))
+        self.lib.check(rc)
+
+    def _chain_stepwise(self, input, output, steps):
+        # Custom(fn) normalisation runs on the host between steps: one call per axis through temporaries
+        cur = input
+        for i, (name, h, ax) in enumerate(steps):
+            op = self._CHAIN_OPS[name]
+            if i == len(steps) - 1:
+                dst = output
+            else:
+                shape = list(cur.shape)
+                if op == _lib.OP_R2C: shape[ax] = h.n // 2 + 1
+                if op == _lib.OP_C2R: shape[ax] = h.n
+                cplx = op in (_lib.OP_FFT, _lib.OP_IFFT, _lib.OP_R2C)
+                cd = np.complex64 if h.dtype == np.float32 else np.complex128
+                if isinstance(cur, np.ndarray):
+                    dst = np.zeros(shape, dtype=cd if cplx else h.dtype)
+                else:
+                    import torch
+                    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                           np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}[np.dtype(cd if cplx else h.dtype)]
+                    dst = torch.zeros(shape, dtype=tdt, device=cur.device)
+            self._run(h, op, cur, dst, ax)
+            cur = dst
+
+    def fft2(self, input, output, handler_ax0, handler_ax1):
+        """examples/fft2.rs:23-27: ndfft along axis 1, then along axis 0."""
+        self.ndchain(input, output, [("ndfft", handler_ax1, 1), ("ndfft", handler_ax0, 0)])
+
+    def ifft2(self, input, output, handler_ax0, handler_ax1):
+        """examples/fft2.rs:55-59: ndifft along axis 0, then along axis 1."""
+        self.ndchain(input, output, [("ndifft", handler_ax0, 0), ("ndifft", handler_ax1, 1)])
+
+    def rfft2(self, input, output, handler_ax0, handler_ax1):
+        """examples/rfft2.rs:29-33: ndfft_r2c along axis 1 (R2cFftHandler), then ndfft along axis 0."""
+        self.ndchain(input, output, [("ndfft_r2c", handler_ax1, 1), ("ndfft", handler_ax0, 0)])
+
+    def irfft2(self, input, output, handler_ax0, handler_ax1):
+        """examples/rfft2.rs:49-53: ndifft along axis 0, then ndifft_r2c along axis 1."""
+        self.ndchain(input, output, [("ndifft", handler_ax0, 0), ("ndifft_r2c", handler_ax1, 1)])
+
     ndfft_par, ndifft_par = ndfft, ndifft
     ndfft_r2c_par, ndifft_r2c_par = ndfft_r2c, ndifft_r2c
     nddct1_par, nddct2_par, nddct3_par, nddct4_par = nddct1, nddct2, nddct3, nddct4
@@ -307,6 +393,11 @@ def nddct1(input, output, handler, axis): handler._backend.nddct1(input, output,
 def nddct2(input, output, handler, axis): handler._backend.nddct2(input, output, handler, axis)
 def nddct3(input, output, handler, axis): handler._backend.nddct3(input, output, handler, axis)
 def nddct4(input, output, handler, axis): handler._backend.nddct4(input, output, handler, axis)
+def ndchain(input, output, steps): steps[0][1]._backend.ndchain(input, output, steps)
+def fft2(input, output, handler_ax0, handler_ax1): handler_ax0._backend.fft2(input, output, handler_ax0, handler_ax1)
+def ifft2(input, output, handler_ax0, handler_ax1): handler_ax0._backend.ifft2(input, output, handler_ax0, handler_ax1)
+def rfft2(input, output, handler_ax0, handler_ax1): handler_ax0._backend.rfft2(input, output, handler_ax0, handler_ax1)
+def irfft2(input, output, handler_ax0, handler_ax1): handler_ax0._backend.irfft2(input, output, handler_ax0, handler_ax1)
 
 
 # `_par` twins (feature "parallel", Cargo.toml:39): on the GPU the serial entry points already run every lane in parallel.

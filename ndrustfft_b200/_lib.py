@@ -25,6 +25,7 @@ E_INVALID, E_SIZE_MISMATCH, E_SHAPE, E_AXIS, E_ALLOC, E_CUDA, E_UNSUPPORTED = -1
 
 EXPORTS = (
     "ndfb_plan_create", "ndfb_plan_destroy", "ndfb_plan_describe", "ndfb_exec", "ndfb_exec_scaled", "ndfb_exec_split_out", "ndfb_exec_scatter_out",
+    "ndfb_exec_chain",
     "ndfb_hint_next_launch_smem", "ndfb_last_error", "ndfb_version", "ndfb_launch_count", "ndfb_release_workspaces",
 )
 
@@ -38,6 +39,11 @@ class NdfftError(RuntimeError):
 
 class SizeMismatch(AssertionError):
     """Mirrors the reference's `assert_size` panic (src/lib.rs:340-347, 533-540, 743-750)."""
+
+
+class Step(ctypes.Structure):
+    """struct ndfb_step (include/ndfft_b200.h)."""
+    _fields_ = [("plan", ctypes.c_void_p), ("op", ctypes.c_int), ("norm", ctypes.c_int), ("axis", ctypes.c_int)]
 
 
 class CLib:
@@ -67,6 +73,8 @@ class CLib:
         d.ndfb_exec_split_out.restype = ci
         d.ndfb_exec_scatter_out.argtypes = [vp, ci, ci, ctypes.c_double, cz, ci, ctypes.POINTER(vp), vp, ci, szp, pdp, szp, pdp, ci, vp]
         d.ndfb_exec_scatter_out.restype = ci
+        d.ndfb_exec_chain.argtypes = [ctypes.POINTER(Step), ci, vp, vp, ci, szp, pdp, szp, pdp, ci, vp]
+        d.ndfb_exec_chain.restype = ci
         d.ndfb_hint_next_launch_smem.argtypes = [cz]
         d.ndfb_hint_next_launch_smem.restype = None
         d.ndfb_last_error.restype = ctypes.c_char_p

@@ -142,7 +142,8 @@ static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
 // ------------------------------------------------------------------------------------------------------
 struct Pool {
     struct Slot { void* p = nullptr; size_t bytes = 0; int device = -1; };
-    Slot slots[7];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows, 5: nested four-step workspace
+    Slot slots[9];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows, 5: nested four-step workspace,
+                     // 7/8: intermediates of ndfb_exec_chain
     ~Pool() {}  // device memory is reclaimed at process exit; explicit release via ndfb_release_workspaces
     int get(int which, int device, size_t bytes, void** out) {
         Slot& s = slots[which];
@@ -1144,6 +1145,190 @@ static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const voi
     return dev_sync(stream);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// multi-axis chains (ndfb_exec_chain): intermediates stay on the device
+// ------------------------------------------------------------------------------------------------------
+struct ChainStep { ndfb_plan* p; OpInfo o; int axis; };
+struct ChainView {
+    void* ptr = nullptr;
+    std::vector<size_t> shape;
+    std::vector<ptrdiff_t> strides;
+    int where = 0;   // 0: caller's input, 1: caller's output, 2/3: workspace slot 7/8
+};
+
+static std::vector<ptrdiff_t> c_strides(const std::vector<size_t>& shape) {
+    std::vector<ptrdiff_t> st(shape.size());
+    long long acc = 1;
+    for (int d = (int)shape.size() - 1; d >= 0; --d) { st[d] = acc; acc *= (long long)shape[d]; }
+    return st;
+}
+
+// Where step i writes: the caller's output as soon as every later step keeps shape and element type (they then run in
+// place on it), else a contiguous workspace (in place on the workspace when the step itself keeps shape and type).
+template <typename R>
+static int chain_dst(const std::vector<ChainStep>& st, int i, const ChainView& src, ChainView* dst, const ChainView& out, int device) {
+    const int n = (int)st.size();
+    bool rest_keeps = true;
+    for (int j = i + 1; j < n; ++j)
+        if (st[j].o.in_complex != st[j].o.out_complex || st[j].o.n_in != st[j].o.n_out) rest_keeps = false;
+    if (i == n - 1 || rest_keeps) { *dst = out; return 0; }
+    const OpInfo& o = st[i].o;
+    const bool keeps = o.in_complex == o.out_complex && o.n_in == o.n_out;
+    if (keeps && src.where >= 2) { *dst = src; return 0; }
+    dst->shape = src.shape;
+    dst->shape[st[i].axis] = (size_t)o.n_out;
+    dst->strides = c_strides(dst->shape);
+    dst->where = src.where == 2 ? 3 : 2;
+    size_t bytes = (o.out_complex ? 2 : 1) * sizeof(R);
+    for (size_t v : dst->shape) bytes *= v;
+    return g_pool.get(dst->where == 2 ? 7 : 8, device, bytes, &dst->ptr);
+}
+
+template <typename R>
+static int chain_device(const std::vector<ChainStep>& st, const ChainView& in, const ChainView& out, stream_t stream,
+                        int first = 0, int last = -1, ChainView* cur_io = nullptr) {
+    // runs steps [first, last]; cur_io carries the current array between partial runs (host pipeline)
+    const int n = (int)st.size();
+    if (last < 0) last = n - 1;
+    ChainView cur = cur_io && first > 0 ? *cur_io : in;
+    for (int i = first; i <= last; ++i) {
+        ChainView dst;
+        int rc = chain_dst<R>(st, i, cur, &dst, out, st[i].p->device);
+        if (rc) return rc;
+        rc = exec_device<R>(st[i].p, st[i].o, 1.0, cur.ptr, dst.ptr, (int)cur.shape.size(), cur.shape.data(), cur.strides.data(),
+                            dst.shape.data(), dst.strides.data(), st[i].axis, stream);
+        if (rc) return rc;
+        cur = dst;
+    }
+    if (cur_io) *cur_io = cur;
+    return 0;
+}
+
+#ifndef NDFB_EMU
+// One chunk [lo, hi) of dim d of a C-ordered array as a 2-D copy (d == 0: one contiguous range; d == 1: shape[0] rows).
+struct ChunkGeom { size_t off, width, rows, pitch; };
+static ChunkGeom chunk_geom(const ChainView& v, int d, size_t lo, size_t hi, size_t elem) {
+    ChunkGeom g;
+    g.off = lo * (size_t)v.strides[d] * elem;
+    g.width = (hi - lo) * (size_t)v.strides[d] * elem;
+    g.rows = d == 0 ? 1 : v.shape[0];
+    g.pitch = d == 0 ? g.width : (size_t)v.strides[0] * elem;
+    return g;
+}
+static int pipeline_pieces(size_t nd, size_t total_bytes, size_t seg_bytes_per_index, bool two_d) {
+    int K = HostPipe::kMaxChunks;
+    if (const char* e = std::getenv("NDFB_HOST_CHUNKS")) return std::max(1, std::min(HostPipe::kMaxChunks, std::min((int)nd, atoi(e))));
+    while (K > 1 && (nd / K < 1 || (total_bytes / K) < (size_t)(2u << 20))) K /= 2;
+    if (two_d) while (K > 2 && (nd / K) * seg_bytes_per_index < (size_t)(16u << 10)) K /= 2;
+    return K;
+}
+
+// Host arrays, >= 2 steps: upload pieces while the first step runs on the pieces already there; middle steps on the
+// whole array; the last step runs piece by piece with the download of the finished pieces behind it.
+template <typename R>
+static int chain_host_pipelined(const std::vector<ChainStep>& st, const void* hin, void* hout, const ChainView& din, const ChainView& dout,
+                                size_t ie, size_t oe, int* done) {
+    *done = 0;
+    const int n = (int)st.size(), ndim = (int)din.shape.size();
+    if (n < 2 || ndim < 2 || std::getenv("NDFB_NO_HOST_PIPELINE")) return 0;
+    if (!is_c_order(ndim, din.shape.data(), din.strides.data()) || !is_c_order(ndim, dout.shape.data(), dout.strides.data())) return 0;
+    size_t total_in = ie, total_out = oe;
+    for (int d = 0; d < ndim; ++d) { total_in *= din.shape[d]; total_out *= dout.shape[d]; }
+    if (total_in + total_out < (size_t)(16u << 20)) return 0;
+    const int d0 = st[0].axis == 0 ? 1 : 0, dl = st[n - 1].axis == 0 ? 1 : 0;
+    const int K0 = pipeline_pieces(din.shape[d0], total_in, (size_t)din.strides[d0] * ie, d0 != 0);
+    const int KL = pipeline_pieces(dout.shape[dl], total_out, (size_t)dout.strides[dl] * oe, dl != 0);
+    if (K0 < 2 || KL < 2) return 0;
+    ndfb_plan* p = st[0].p;
+    int rc = g_pipe.init(p->device);
+    if (rc) return rc;
+    // first step, piece by piece behind the upload
+    ChainView d1;
+    if ((rc = chain_dst<R>(st, 0, din, &d1, dout, p->device))) return rc;
+    const size_t e1 = (st[0].o.out_complex ? 2 : 1) * sizeof(R);
+    {
+        const size_t nd = din.shape[d0];
+        ChainView a = din, b = d1;
+        for (int c = 0; c < K0; ++c) {
+            const size_t lo = nd * c / K0, hi = nd * (c + 1) / K0;
+            if (hi == lo) continue;
+            const ChunkGeom g = chunk_geom(din, d0, lo, hi, ie);
+            NDFB_CUDA(cudaMemcpy2DAsync((char*)din.ptr + g.off, g.pitch, (const char*)hin + g.off, g.pitch, g.width, g.rows, cudaMemcpyHostToDevice, g_pipe.s[0]));
+            NDFB_CUDA(cudaEventRecord(g_pipe.ev_in[c], g_pipe.s[0]));
+            NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ev_in[c], 0));
+            a.shape[d0] = b.shape[d0] = hi - lo;
+            rc = exec_device<R>(p, st[0].o, 1.0, (const char*)din.ptr + g.off, (char*)d1.ptr + lo * (size_t)d1.strides[d0] * e1, ndim,
+                                a.shape.data(), a.strides.data(), b.shape.data(), b.strides.data(), st[0].axis, g_pipe.s[1]);
+            if (rc) { cudaDeviceSynchronize(); return rc; }
+        }
+    }
+    // middle steps on the whole array
+    ChainView cur = d1;
+    if (n > 2 && (rc = chain_device<R>(st, din, dout, g_pipe.s[1], 1, n - 2, &cur))) { cudaDeviceSynchronize(); return rc; }
+    // last step, piece by piece ahead of the download
+    {
+        const ChainStep& L = st[n - 1];
+        const size_t el = (L.o.in_complex ? 2 : 1) * sizeof(R);
+        const size_t nd = dout.shape[dl];
+        ChainView a = cur, b = dout;
+        for (int c = 0; c < KL; ++c) {
+            const size_t lo = nd * c / KL, hi = nd * (c + 1) / KL;
+            if (hi == lo) continue;
+            const ChunkGeom g = chunk_geom(dout, dl, lo, hi, oe);
+            a.shape[dl] = b.shape[dl] = hi - lo;
+            rc = exec_device<R>(L.p, L.o, 1.0, (const char*)cur.ptr + lo * (size_t)cur.strides[dl] * el, (char*)dout.ptr + g.off, ndim,
+                                a.shape.data(), a.strides.data(), b.shape.data(), b.strides.data(), L.axis, g_pipe.s[1]);
+            if (rc) { cudaDeviceSynchronize(); return rc; }
+            NDFB_CUDA(cudaEventRecord(g_pipe.ev_k[c], g_pipe.s[1]));
+            NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[2], g_pipe.ev_k[c], 0));
+            NDFB_CUDA(cudaMemcpy2DAsync((char*)hout + g.off, g.pitch, (const char*)dout.ptr + g.off, g.pitch, g.width, g.rows, cudaMemcpyDeviceToHost, g_pipe.s[2]));
+        }
+    }
+    NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[2]));
+    NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[1]));
+    *done = 1;
+    return 0;
+}
+#endif
+
+template <typename R>
+static int chain_any(const std::vector<ChainStep>& st, const void* in, void* out, int ndim, const size_t* shape_in,
+                     const ptrdiff_t* strides_in, const size_t* shape_out, const ptrdiff_t* strides_out, int mem, void* stream_v) {
+    stream_t stream = (stream_t)stream_v;
+    ndfb_plan* p = st[0].p;
+    int rc = dev_set(p->device);
+    if (rc) return rc;
+    ChainView vi, vo;
+    vi.shape.assign(shape_in, shape_in + ndim); vi.strides.assign(strides_in, strides_in + ndim); vi.where = 0;
+    vo.shape.assign(shape_out, shape_out + ndim); vo.strides.assign(strides_out, strides_out + ndim); vo.where = 1;
+    if (mem == NDFB_MEM_DEVICE) {
+        vi.ptr = const_cast<void*>(in); vo.ptr = out;
+        return chain_device<R>(st, vi, vo, stream);
+    }
+    const size_t ie = (st.front().o.in_complex ? 2 : 1) * sizeof(R), oe = (st.back().o.out_complex ? 2 : 1) * sizeof(R);
+    long long ilo, ihi, olo, ohi;
+    bool idense, odense;
+    span_of(ndim, shape_in, strides_in, ie, &ilo, &ihi, &idense);
+    span_of(ndim, shape_out, strides_out, oe, &olo, &ohi, &odense);
+    if (ihi == ilo || ohi == olo) return 0;
+    void *din = nullptr, *dout = nullptr;
+    if ((rc = g_pool.get(0, p->device, (size_t)(ihi - ilo), &din))) return rc;
+    if ((rc = g_pool.get(1, p->device, (size_t)(ohi - olo), &dout))) return rc;
+    vi.ptr = (char*)din - ilo; vo.ptr = (char*)dout - olo;
+#ifndef NDFB_EMU
+    {
+        int done = 0;
+        rc = chain_host_pipelined<R>(st, in, out, vi, vo, ie, oe, &done);
+        if (rc || done) return rc;
+    }
+#endif
+    if ((rc = dev_h2d(din, (const char*)in + ilo, (size_t)(ihi - ilo), stream))) return rc;
+    if (!odense && (rc = dev_h2d(dout, (const char*)out + olo, (size_t)(ohi - olo), stream))) return rc;
+    if ((rc = chain_device<R>(st, vi, vo, stream))) return rc;
+    if ((rc = dev_d2h((char*)out + olo, dout, (size_t)(ohi - olo), stream))) return rc;
+    return dev_sync(stream);
+}
+
 }  // namespace ndfb
 
 // ------------------------------------------------------------------------------------------------------
@@ -1256,6 +1441,50 @@ int ndfb_exec(const ndfb_plan* plan, int op, int norm, const void* in, void* out
               const ptrdiff_t* strides_in, const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem,
               void* stream) {
     return ndfb_exec_scaled(plan, op, norm, 1.0, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+}
+
+int ndfb_exec_chain(const ndfb_step* steps, int nsteps, const void* in, void* out, int ndim, const size_t* shape_in,
+                    const ptrdiff_t* strides_in, const size_t* shape_out, const ptrdiff_t* strides_out, int mem, void* stream) {
+    if (!steps || nsteps < 1 || nsteps > 16) return fail(NDFB_E_INVALID, "1..16 steps expected");
+    if (!shape_in || !strides_in || !shape_out || !strides_out) return fail(NDFB_E_INVALID, "null argument");
+    if (ndim < 1 || ndim > NDFB_MAX_DIMS) return fail(NDFB_E_INVALID, "ndim %d outside 1..%d", ndim, NDFB_MAX_DIMS);
+    if (mem != NDFB_MEM_HOST && mem != NDFB_MEM_DEVICE) return fail(NDFB_E_INVALID, "unknown mem %d", mem);
+    DeviceGuard device_guard;
+    (void)device_guard;
+    std::vector<ChainStep> st(nsteps);
+    std::vector<size_t> cur(shape_in, shape_in + ndim);
+    bool cur_complex = false;
+    for (int i = 0; i < nsteps; ++i) {
+        const ndfb_step& s = steps[i];
+        if (!s.plan) return fail(NDFB_E_INVALID, "step %d: null plan", i);
+        if (s.norm != NDFB_NORM_NONE && s.norm != NDFB_NORM_DEFAULT) return fail(NDFB_E_INVALID, "step %d: unknown norm %d", i, s.norm);
+        st[i].p = const_cast<ndfb_plan*>(s.plan);
+        st[i].axis = s.axis;
+        if (st[i].p->dtype != st[0].p->dtype || st[i].p->device != st[0].p->device)
+            return fail(NDFB_E_INVALID, "step %d: all plans of a chain must share dtype and device", i);
+        int rc = op_info(st[i].p, s.op, s.norm, &st[i].o);
+        if (rc) return rc;
+        const OpInfo& o = st[i].o;
+        if (s.axis < 0 || s.axis >= ndim) return fail(NDFB_E_AXIS, "axis %d out of range for %d-dimensional array", s.axis, ndim);
+        if (i > 0 && o.in_complex != cur_complex)
+            return fail(NDFB_E_INVALID, "step %d reads %s data but step %d wrote %s data", i, o.in_complex ? "complex" : "real", i - 1, cur_complex ? "complex" : "real");
+        if ((long long)cur[s.axis] != o.n_in)
+            return fail(NDFB_E_SIZE_MISMATCH, "Size mismatch in %s, got %zu expected %lld", o.what, cur[s.axis], o.n_in);
+        cur[s.axis] = (size_t)o.n_out;
+        cur_complex = o.out_complex;
+    }
+    for (int d = 0; d < ndim; ++d) {
+        if (cur[d] == shape_out[d]) continue;
+        bool transformed = false;
+        const char* what = "fft";
+        for (auto& c : st) if (c.axis == d) { transformed = true; what = c.o.what; }
+        if (transformed) return fail(NDFB_E_SIZE_MISMATCH, "Size mismatch in %s, got %zu expected %zu", what, shape_out[d], cur[d]);
+        return fail(NDFB_E_SHAPE, "input and output shapes differ along dimension %d (%zu vs %zu)", d, shape_in[d], shape_out[d]);
+    }
+    for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) return NDFB_OK;
+    if (!in || !out) return fail(NDFB_E_INVALID, "null data pointer");
+    if (st[0].p->dtype == NDFB_F32) return chain_any<float>(st, in, out, ndim, shape_in, strides_in, shape_out, strides_out, mem, stream);
+    return chain_any<double>(st, in, out, ndim, shape_in, strides_in, shape_out, strides_out, mem, stream);
 }
 
 size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {

@@ -170,6 +170,62 @@ class Harness:
             be.ndfft(v, vhat, h, 0); be.ndifft(vhat, v2, h, 0)
             approx(v2, np.array(g[key]) * (1 + 1j), 1e-12)
 
+    # ---- multi-axis chains (ndfb_exec_chain) vs the same steps through the oracle, one call per axis ----
+    def run_chain(self, steps, shape_in, rd=np.float64, norm="default", seed=0, inplace=False, tol=None):
+        """steps = [(op name, n, axis)]; returns the relative L2 error against the oracle's step-by-step result."""
+        rd = np.dtype(rd)
+        icx = self.OPS[steps[0][0]][1]
+        x = seeded(seed, shape_in, rd, icx)
+        hs, cur = [], x.astype(np.complex128 if icx else np.float64)
+        for op, n, axis in steps:
+            hk, _, ocx = self.OPS[op]
+            h = getattr(self.be, hk)(n, rd)
+            ho = getattr(orc, hk)(n)
+            if norm == "none":
+                h.normalization(type(h.norm).None_)
+                ho.normalization(orc.Normalization.none())
+            hs.append((op, h, axis))
+            _, sout = self.shapes(op, n, cur.shape, axis)
+            nxt = np.zeros(sout, np.complex128 if ocx else np.float64)
+            getattr(orc, op)(cur, nxt, ho, axis)
+            cur = nxt
+        ocx = self.OPS[steps[-1][0]][2]
+        xin = self.mk(x)
+        y = xin if inplace else self.zeros(cur.shape, cdt(rd) if ocx else rd)
+        self.be.ndchain(xin, y, hs)
+        err = orc.rel_l2(self.to_np(y), cur)
+        if not inplace:
+            assert np.array_equal(self.to_np(xin), x), "input was modified"
+        t = TOL[rd] if tol is None else tol
+        assert err <= t, f"chain {steps} shape={shape_in} {rd} norm={norm}: rel L2 {err:.3e} > {t:g}"
+        return err
+
+    def chain_examples(self):
+        """examples/fft2.rs and examples/rfft2.rs through the fused entry points."""
+        be = self.be
+
+        def approx(a, b, t):
+            assert np.max(np.abs(self.to_np(a) - np.asarray(b))) <= t
+
+        g = G["example_fft2"]
+        v = self.mk(np.array(g["input_real"]) * (1 + 1j))
+        vhat = self.zeros((3, 3), np.complex128); v2 = self.zeros((3, 3), np.complex128)
+        h0, h1 = be.FftHandler(3), be.FftHandler(3)
+        be.fft2(v, vhat, h0, h1)
+        want = np.array(g["numpy_vhat"])
+        approx(vhat, want[..., 0] + 1j * want[..., 1], g["tol"])
+        be.ifft2(vhat, v2, h0, h1)
+        approx(v2, np.array(g["input_real"]) * (1 + 1j), g["tol"])
+        g = G["example_rfft2"]
+        v = self.mk(np.array(g["input_real"]))
+        vhat = self.zeros((3, 2), np.complex128); v2 = self.zeros((3, 3), np.float64)
+        h0, h1 = be.FftHandler(3), be.R2cFftHandler(3)
+        be.rfft2(v, vhat, h0, h1)
+        want = np.array(g["numpy_vhat"])
+        approx(vhat, want[..., 0] + 1j * want[..., 1], g["tol"])
+        be.irfft2(vhat, v2, h0, h1)
+        approx(v2, np.array(g["input_real"]), g["tol"])
+
     def mk_f(self, a):
         """An F-ordered array (host: numpy asfortranarray; device harness overrides)."""
         return np.asfortranarray(np.array(a))

@@ -395,3 +395,94 @@ def test_bsfft_and_general_bluestein_agree(hs, capfd):
         del os.environ["NDFB_DISABLE_BSFFT"]
         del os.environ["NDFB_TRACE"]
     assert "[ndfb] bsfft" not in capfd.readouterr().err
+
+
+# ---- multi-axis chains (ndfb_exec_chain): intermediates in `out` or in library workspaces ----
+def test_chain_reference_examples(hs):
+    hs.chain_examples()
+
+
+@pytest.mark.parametrize("rd", [np.float64, np.float32])
+def test_chain_fft_rfft_nd(hs, rd):
+    hs.run_chain([("ndfft", 12, 1), ("ndfft", 10, 0)], (10, 12), rd, seed=1)                              # fft2: second step in place on out
+    hs.run_chain([("ndifft", 10, 0), ("ndifft", 12, 1)], (10, 12), rd, seed=2)
+    hs.run_chain([("ndfft_r2c", 16, 2), ("ndfft", 6, 1), ("ndfft", 5, 0)], (5, 6, 16), rd, seed=3)       # rfft3 (config 3 pattern)
+    hs.run_chain([("ndifft", 5, 0), ("ndifft", 6, 1), ("ndifft_r2c", 16, 2)], (5, 6, 9), rd, seed=4)     # irfft3: workspace, in place on it
+    hs.run_chain([("ndifft", 5, 0), ("ndifft_r2c", 9, 1)], (5, 5), rd, seed=5, norm="none")              # odd real length
+    hs.run_chain([("ndfft", 64, 0)], (64, 3), rd, seed=6)                                                  # single step = plain call
+
+
+def test_chain_dct_and_mixed(hs):
+    hs.run_chain([("nddct2", 8, 0), ("nddct3", 8, 0)], (8, 5), seed=1)                                   # 2n * x
+    hs.run_chain([("nddct1", 9, 1), ("nddct4", 6, 0), ("nddct2", 4, 2)], (6, 9, 4), seed=2)
+    hs.run_chain([("nddct2", 10, 0), ("ndfft_r2c", 12, 1)], (10, 12), seed=3)                             # Chebyshev x Fourier
+    hs.run_chain([("ndfft_r2c", 12, 1), ("ndifft_r2c", 12, 1)], (4, 12), seed=4)                          # real -> complex -> real
+    hs.run_chain([("ndfft_r2c", 8, 1), ("ndfft", 6, 0), ("ndifft", 6, 0), ("ndifft_r2c", 8, 1)], (6, 8), seed=5)
+
+
+def test_chain_in_place(hs):
+    hs.run_chain([("ndfft", 12, 1), ("ndfft", 10, 0)], (10, 12), seed=1, inplace=True)
+    hs.run_chain([("nddct2", 16, 0)], (16, 4), seed=2, inplace=True)
+    hs.run("ndfft", 64, (64, 3), 0)  # (single calls in place are covered below)
+
+
+@pytest.mark.parametrize("op,n,shape,axis", [("ndfft", 360, (3, 360), 1), ("ndifft", 64, (64, 5), 0), ("nddct1", 9, (9, 3), 0),
+                                              ("nddct4", 12, (2, 12), 1), ("ndfft", 1009, (2, 1009), 1), ("ndfft", 17, (17, 4), 0)])
+def test_single_call_in_place(hs, op, n, shape, axis):
+    import oracle.ndrustfft_oracle as orc
+    from parity_cases import seeded
+    icx = hs.OPS[op][1]
+    x = seeded(3, shape, np.float64, icx)
+    h = getattr(hs.be, hs.OPS[op][0])(n)
+    ho = getattr(orc, hs.OPS[op][0])(n)
+    want = np.zeros(shape, np.complex128 if icx else np.float64)
+    getattr(orc, op)(x, want, ho, axis)
+    buf = hs.mk(x)
+    getattr(hs.be, op)(buf, buf, h, axis)
+    assert orc.rel_l2(hs.to_np(buf), want) <= 1e-12
+
+
+def test_chain_in_place_four_step(hs):
+    import os
+    os.environ["NDFB_FORCE_FOUR_STEP"] = "1"
+    try:
+        hs.run_chain([("ndfft", 64, 1), ("ndfft", 36, 0)], (36, 64), seed=1, inplace=True)
+    finally:
+        del os.environ["NDFB_FORCE_FOUR_STEP"]
+
+
+def test_chain_errors(hs):
+    from ndrustfft_b200 import SizeMismatch, NdfftError
+    be = hs.be
+    x = np.zeros((4, 6), np.complex128); y = np.zeros((4, 6), np.complex128)
+    with pytest.raises(SizeMismatch, match="Size mismatch in fft, got 6 expected 5"):
+        be.ndchain(x, y, [("ndfft", be.FftHandler(5), 1), ("ndfft", be.FftHandler(4), 0)])
+    with pytest.raises(SizeMismatch, match="Size mismatch in fft, got 4 expected 3"):
+        be.ndchain(x, y, [("ndfft", be.FftHandler(6), 1), ("ndfft", be.FftHandler(3), 0)])
+    with pytest.raises(IndexError):
+        be.ndchain(x, y, [("ndfft", be.FftHandler(6), 2)])
+    xr = np.zeros((4, 6)); yc = np.zeros((4, 6), np.complex128)
+    with pytest.raises(SizeMismatch, match="Size mismatch in fft, got 6 expected 4"):
+        be.ndchain(xr, yc, [("ndfft_r2c", be.R2cFftHandler(6), 1)])
+    with pytest.raises(NdfftError, match="reads real data"):
+        be.ndchain(x, np.zeros((4, 6)), [("ndfft", be.FftHandler(6), 1), ("nddct2", be.DctHandler(4), 0)])
+    with pytest.raises(NdfftError, match="share dtype"):
+        be.ndchain(x, y, [("ndfft", be.FftHandler(6), 1), ("ndfft", be.FftHandler(4, np.float32), 0)])
+    with pytest.raises(ValueError):
+        be.ndchain(x, y, [])
+
+
+def test_chain_custom_normalisation_falls_back_to_single_calls(hs):
+    be = hs.be
+    Norm = type(be.FftHandler(3).norm)
+
+    def my_norm(lane):
+        lane *= 0.5
+
+    rng = np.random.default_rng(0)
+    x = (rng.uniform(-1, 1, (6, 8)) + 1j * rng.uniform(-1, 1, (6, 8)))
+    y = np.zeros_like(x); want = np.zeros_like(x); work = np.zeros_like(x)
+    h0, h1 = be.FftHandler(6).normalization(Norm.Custom(my_norm)), be.FftHandler(8)
+    be.ndchain(x, y, [("ndifft", h0, 0), ("ndifft", h1, 1)])
+    be.ndifft(x, work, h0, 0); be.ndifft(work, want, h1, 1)
+    assert np.allclose(y, want, rtol=0, atol=1e-14)

@@ -418,3 +418,76 @@ def test_current_device_is_restored(dev):
     before = torch.cuda.current_device()
     dev.run("ndfft", 64, (4, 64), 1)
     assert torch.cuda.current_device() == before
+
+
+# ---- multi-axis chains (ndfb_exec_chain): same result as the single calls, intermediates on the device ----
+def test_chain_examples_device_and_host(dev, host):
+    dev.chain_examples()
+    host.chain_examples()
+
+
+@pytest.mark.parametrize("rd", [np.float64, np.float32])
+def test_chain_small_device_and_host(dev, host, rd):
+    for h in (dev, host):
+        h.run_chain([("ndfft", 360, 1), ("ndfft", 100, 0)], (100, 360), rd, seed=1)
+        h.run_chain([("ndfft_r2c", 128, 2), ("ndfft", 60, 1), ("ndfft", 36, 0)], (36, 60, 128), rd, seed=2)
+        h.run_chain([("ndifft", 36, 0), ("ndifft", 60, 1), ("ndifft_r2c", 128, 2)], (36, 60, 65), rd, seed=3)
+        h.run_chain([("nddct1", 129, 1), ("nddct2", 64, 0)], (64, 129), rd, seed=4)
+        h.run_chain([("ndfft", 1009, 1), ("ndfft", 17, 0)], (17, 1009), rd, seed=5)
+    dev.run_chain([("ndfft", 1024, 1), ("ndfft", 512, 0)], (512, 1024), rd, seed=6, inplace=True)
+
+
+def test_chain_host_pipelined_matches_single_calls(host, dev):
+    # 2048 x 4096 c64 = 64 MiB each way: large enough for the pipelined host path (pieces of the first step behind the
+    # upload, pieces of the last step ahead of the download); compare with the two single device calls
+    be = host.be
+    rng = np.random.default_rng(7)
+    x = (rng.uniform(-1, 1, (2048, 4096)) + 1j * rng.uniform(-1, 1, (2048, 4096))).astype(np.complex64)
+    y = np.zeros_like(x)
+    h0, h1 = be.FftHandler(2048, np.float32), be.FftHandler(4096, np.float32)
+    be.fft2(x, y, h0, h1)
+    xd = torch.from_numpy(x).cuda(); w = torch.empty_like(xd); yd = torch.empty_like(xd)
+    be.ndfft(xd, w, h1, 1); be.ndfft(w, yd, h0, 0)
+    assert np.array_equal(y, yd.cpu().numpy())          # same kernels, same order: bit-identical
+    want = np.fft.fft2(x.astype(np.complex128))
+    assert orc.rel_l2(y, want) <= 1e-5
+    # rfft3-style chain with a shape change and a 3-D array (pieces are 2-D copies when axis 0 is transformed last)
+    xr = rng.uniform(-1, 1, (128, 256, 512))
+    yr = np.zeros((128, 256, 257), np.complex128)
+    hr, hb, ha = be.R2cFftHandler(512), be.FftHandler(256), be.FftHandler(128)
+    be.ndchain(xr, yr, [("ndfft_r2c", hr, 2), ("ndfft", hb, 1), ("ndfft", ha, 0)])
+    assert orc.rel_l2(yr, np.fft.rfftn(xr)) <= 1e-12
+    back = np.zeros_like(xr)
+    be.ndchain(yr, back, [("ndifft", ha, 0), ("ndifft", hb, 1), ("ndifft_r2c", hr, 2)])
+    assert orc.rel_l2(back, xr) <= 1e-12
+
+
+def test_chain_config3_device(dev):
+    # c3 as one call: 512^3 f64 -> 512 x 512 x 257 c128, intermediates live in the output array (two in-place passes)
+    be = dev.be
+    n = 512
+    x = _rand((n, n, n), np.float64, False, 0xB200 + 49)
+    hr = be.R2cFftHandler(n); hc = be.FftHandler(n)
+    c = torch.empty((n, n, n // 2 + 1), dtype=torch.complex128, device="cuda")
+    be.ndchain(x, c, [("ndfft_r2c", hr, 2), ("ndfft", hc, 1), ("ndfft", hc, 0)])
+    a = torch.empty_like(c); b = torch.empty_like(c)
+    be.ndfft_r2c(x, a, hr, 2); be.ndfft(a, b, hc, 1); be.ndfft(b, a, hc, 0)
+    assert torch.equal(a, c)
+    back = torch.empty_like(x)
+    be.ndchain(c, back, [("ndifft", hc, 0), ("ndifft", hc, 1), ("ndifft_r2c", hr, 2)])
+    assert _rel(back, x) < 1e-12
+
+
+@pytest.mark.parametrize("op,n,shape,axis", [("ndfft", 8192, (64, 8192), 1), ("ndifft", 8192, (8192, 64), 0), ("ndfft", 1 << 20, (2, 1 << 20), 1),
+                                              ("nddct1", 4096, (4096, 32), 0), ("nddct3", 4096, (16, 4096), 1), ("ndfft", 1009, (1009, 40), 0)])
+def test_single_call_in_place_device(dev, op, n, shape, axis):
+    be = dev.be
+    icx = Harness.OPS[op][1]
+    rd = np.float32 if n >= 8192 else np.float64
+    x = _rand(shape, rd, icx, 11)
+    h = getattr(be, Harness.OPS[op][0])(n, rd)
+    want = torch.empty_like(x)
+    getattr(be, op)(x, want, h, axis)
+    buf = x.clone()
+    getattr(be, op)(buf, buf, h, axis)
+    assert torch.equal(buf, want)
