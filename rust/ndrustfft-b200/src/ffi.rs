@@ -24,6 +24,16 @@ pub const NDFB_NORM_DEFAULT: c_int = 1;
 pub const NDFB_MEM_HOST: c_int = 0;
 pub const NDFB_MEM_DEVICE: c_int = 1;
 
+/// `struct ndfb_step` of the C header.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct NdfbStep {
+    pub plan: *const NdfbPlan,
+    pub op: c_int,
+    pub norm: c_int,
+    pub axis: c_int,
+}
+
 extern "C" {
     pub fn ndfb_plan_create(out: *mut *mut NdfbPlan, kind: c_int, dtype: c_int, n: usize, device: c_int) -> c_int;
     pub fn ndfb_plan_destroy(plan: *mut NdfbPlan);
@@ -36,6 +46,12 @@ extern "C" {
         plan: *const NdfbPlan, op: c_int, norm: c_int, extra_scale: c_double, input: *const c_void,
         output: *mut c_void, ndim: c_int, shape_in: *const usize, strides_in: *const isize,
         shape_out: *const usize, strides_out: *const isize, axis: c_int, mem: c_int, stream: *mut c_void,
+    ) -> c_int;
+    /// Multi-axis chain (include/ndfft_b200.h: ndfb_exec_chain); `steps` points at `nsteps` NdfbStep records.
+    pub fn ndfb_exec_chain(
+        steps: *const NdfbStep, nsteps: c_int, input: *const c_void, output: *mut c_void, ndim: c_int,
+        shape_in: *const usize, strides_in: *const isize, shape_out: *const usize, strides_out: *const isize,
+        mem: c_int, stream: *mut c_void,
     ) -> c_int;
     pub fn ndfb_last_error() -> *const c_char;
     pub fn ndfb_version() -> *const c_char;
