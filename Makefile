@@ -8,7 +8,7 @@ LIBDIR    := ndrustfft_b200/lib
 LIB       := $(LIBDIR)/libndfft_b200.so
 EMULIB    := tests/emu/libndfft_b200_emu.so
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-fvisibility=hidden \
-             --expt-relaxed-constexpr -cudart shared
+             --expt-relaxed-constexpr -cudart shared $(EXTRA)
 CXXFLAGS  := -O2 -g -std=c++17 -fPIC -DNDFB_EMU -Itests/emu
 OBJDIR    := build
 NVOBJS    := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/cuda/%.o,$(SRCS))

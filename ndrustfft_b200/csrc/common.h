@@ -48,6 +48,36 @@ NDFB_DEV Cx<double> ldg(const Cx<double>* p) {
 NDFB_DEV uint32_t ldg(const uint32_t* p) { return __ldg(p); }
 #endif
 
+// streaming loads of the user's array: each element is read once, so it should not displace the twiddle tables from L1
+// (the 8192-point row kernel re-read 17 M twiddle sectors per launch from L2 before; profiles/r1l_ncu_bench_summary.txt)
+#ifndef NDFB_STREAM_LD
+#define NDFB_STREAM_LD 0   // measured neutral on B200 (profiles/r1q_ab_stream.jsonl): off
+#endif
+#if defined(NDFB_EMU) || !NDFB_STREAM_LD
+template <typename T> NDFB_DEV T ld_stream(const T* p) { return *p; }
+#else
+NDFB_DEV Cx<float> ld_stream(const Cx<float>* p) {
+    float x, y;
+    asm("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p) : "memory");
+    return cmake<float>(x, y);
+}
+NDFB_DEV Cx<double> ld_stream(const Cx<double>* p) {
+    double x, y;
+    asm("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
+    return cmake<double>(x, y);
+}
+NDFB_DEV float ld_stream(const float* p) {
+    float x;
+    asm("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(x) : "l"(p) : "memory");
+    return x;
+}
+NDFB_DEV double ld_stream(const double* p) {
+    double x;
+    asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(x) : "l"(p) : "memory");
+    return x;
+}
+#endif
+
 // What one launch of the tile kernel computes around its forward complex FFT core of length N.
 // (n = the handler's logical length; see DESIGN.md "kinds" for the algebra, verified in tests/kernel_math_model.py.)
 enum TileKind : int {

@@ -633,10 +633,13 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
                 continue;
             }
             const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
-            const SfftEntry* e2 = find_sfft(sizeof(R) == 8, (int)n2, strided_lanes, 1 << 20);
+            // pass 2 stores out[k1 + N1*k2]: its OUTPUT is lane-interleaved in both variants, so it runs the column
+            // layout and wants a tile at least one sector wide too (2^24 f32 x 64: 2048 x 8192 14.6 ms, 4096 x 4096 12.4 ms)
+            const SfftEntry* e2 = find_sfft(sizeof(R) == 8, (int)n2, true, 1 << 20);
             if (e1 && (size_t)e1->L * cs >= 32) score += 2;
             if (e1 && (size_t)e1->L * cs >= 64) score += 1;
-            if (e2 && (!strided_lanes || (size_t)e2->L * cs >= 32)) score += 2;
+            if (e2 && (size_t)e2->L * cs >= 32) score += 2;
+            if (e2 && (size_t)e2->L * cs >= 64) score += 1;
             if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
     }

@@ -15,6 +15,10 @@
 #include "butterflies.cuh"
 #include "common.h"
 
+#ifndef NDFB_TW_POW
+#define NDFB_TW_POW 1   // +2..10 % on B200 (profiles/r1r_ab_twiddle_powers.jsonl: A = table loads, B = powers)
+#endif
+
 namespace ndfb {
 
 struct SfftArgs {
@@ -131,8 +135,23 @@ struct SfftPass {
                 const int k = KCONST ? k0 : b % P;
                 if (!FIRST) {
                     const Cx<R>* __restrict__ twp = KCONST ? twp0 : tw + S::twoff(PASS) + k;
+#if NDFB_TW_POW
+                    if constexpr (r >= 8 && (r & (r - 1)) == 0 && (S::N & (S::N - 1)) == 0) {
+                        // load W^k, W^2k, W^4k, W^8k and form the other powers as products (depth <= 3): 4 table loads, not 15
+                        Cx<R> t[r];
 #pragma unroll
-                    for (int q = 1; q < r; ++q) v[m * r + q] = cmul(v[m * r + q], ldg(&twp[(q - 1) * P]));
+                        for (int q = 1; q < r; ++q) {
+                            int hb = 1;
+                            while (hb * 2 <= q) hb *= 2;
+                            t[q] = (hb == q) ? ldg(&twp[(q - 1) * P]) : cmul(t[hb], t[q - hb]);
+                            v[m * r + q] = cmul(v[m * r + q], t[q]);
+                        }
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int q = 1; q < r; ++q) v[m * r + q] = cmul(v[m * r + q], ldg(&twp[(q - 1) * P]));
+                    }
                 }
                 Dft<R, r>::run(&v[m * r]);
                 if (LAST) {
@@ -223,7 +242,7 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     const int j2 = lb.j2;
     Cx<R> v[S::E];
     auto load = [&](int j) -> Cx<R> {
-        Cx<R> x = valid ? in[(long long)j * is_axis] : cmake<R>((R)0, (R)0);
+        Cx<R> x = valid ? ld_stream(&in[(long long)j * is_axis]) : cmake<R>((R)0, (R)0);
         x.y *= sgn_in;
         return x;
     };
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(S::TL* L, MINB) bsfft_kernel(const __grid_cons
     Cx<R> v[S::E];
     auto load1 = [&](int j) -> Cx<R> {
         if (j >= N || !valid) return cmake<R>(zero, zero);
-        Cx<R> x = in[(long long)j * is_axis];
+        Cx<R> x = ld_stream(&in[(long long)j * is_axis]);
         x.y *= sgn_in;
         return cmul(x, ldg(&chirp[j]));
     };
@@ -397,7 +416,7 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
         // plain complex slots (conflict free):  DCT-II: Makhoul order v[p(t)];  DCT-IV: u[j] = (x[2j], x[n-1-2j])
         for (int t = c.i; t < n; t += S::TL) {
             const int pos = KIND == RK_DCT2 ? ((t & 1) ? n - 1 - (t >> 1) : (t >> 1)) : ((t & 1) ? n - t : t);
-            sreal(pos) = gin(t);
+            sreal(pos) = valid ? ld_stream(&in_r[(long long)t * is_axis]) : zero;
         }
         __syncthreads();
     }
