@@ -611,6 +611,38 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     // column pass, a tile at least one 32-byte sector wide), then the most square split
     normalize_dims(dims);
     const bool strided_lanes = !dims.empty() && llabs_(dims[0].is) < llabs_(is_axis) && llabs_(dims[0].os) < llabs_(os_axis);
+    // Optional L2-resident workspace (NDFB_FS_L2_KB=<group size>; off by default): run the two passes group by group over
+    // a slice of the lanes and reuse ONE workspace, so that pass 2 reads what pass 1 just wrote from L2 and the two-pass
+    // transform costs one HBM round trip.  Measured on B200 (profiles/r1t_l2_groups.jsonl): the DRAM traffic does halve,
+    // but 32-64 MB groups are 15-25 us kernels of 2-4 waves whose ramp-up and tail cost more than the saved pass
+    // (c2 axis 0: 0.37 ms ungrouped, 0.42 ms in 64 MB groups even replayed from a CUDA graph) -- it needs a persistent
+    // two-pass kernel with device-side group dependencies to pay off.
+    if (depth == 0 && !dims.empty()) {
+        size_t target = 0;
+        if (const char* e = std::getenv("NDFB_FS_L2_KB")) target = (size_t)atoll(e) << 10;   // 0 disables; tests shrink it
+        long long nb_all = 1;
+        for (auto& d : dims) nb_all *= d.size;
+        const size_t lane_bytes = (size_t)N * cs;
+        if (target && (size_t)nb_all * lane_bytes > target + target / 2) {
+            // slice the outermost batch dim; a single index of it may still be too big (then the recursion slices the next)
+            const int cd = (int)dims.size() - 1;
+            long long inner = nb_all / dims[cd].size;
+            long long per = (long long)(target / ((size_t)inner * lane_bytes));     // indices of dim cd per group
+            const bool innermost_cols = strided_lanes && cd == 0;
+            if (innermost_cols) per = per / 64 * 64;                                // keep whole 512-byte column groups
+            if (per < 1 && cd > 0) per = 1;
+            if (per >= 1 && per < dims[cd].size && (!innermost_cols || per >= 64)) {
+                for (long long c0 = 0; c0 < dims[cd].size; c0 += per) {
+                    std::vector<BDim> sub = dims;
+                    sub[cd].size = std::min(per, dims[cd].size - c0);
+                    int rc = exec_four_step<R>(p, N, inverse, scale, (const char*)in + c0 * dims[cd].is * (long long)cs,
+                                               (char*)out + c0 * dims[cd].os * (long long)cs, sub, is_axis, os_axis, stream, 0, conj_in_override);
+                    if (rc) return rc;
+                }
+                return 0;
+            }
+        }
+    }
     long long best1 = 0;
     int best_score = -1;
     for (long long d = 1; d * d <= N; ++d) {

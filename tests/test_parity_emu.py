@@ -486,3 +486,25 @@ def test_chain_custom_normalisation_falls_back_to_single_calls(hs):
     be.ndchain(x, y, [("ndifft", h0, 0), ("ndifft", h1, 1)])
     be.ndifft(x, work, h0, 0); be.ndifft(work, want, h1, 1)
     assert np.allclose(y, want, rtol=0, atol=1e-14)
+
+
+def test_four_step_l2_groups(hs, capfd):
+    """Two-pass transforms run group by group over a reused workspace (L2-resident on the GPU); NDFB_FS_L2_KB shrinks the
+    group size so the emulator exercises the slicing of the innermost column dim, of outer batch dims and of both."""
+    import os
+    os.environ.update({"NDFB_FORCE_FOUR_STEP": "1", "NDFB_FS_L2_KB": "64", "NDFB_TRACE": "1"})
+    try:
+        hs.run("ndfft", 64, (64, 200), 0, np.float32, seed=1)            # strided columns: 64 x 200 x 8 B = 100 KB -> column groups of 128
+        n1 = capfd.readouterr().err.count("[ndfb] four-step")
+        hs.run("ndifft", 256, (12, 256, 3), 1, np.float64, seed=2)       # outer dim sliced (5 + 5 + 2), 3 columns kept together
+        n2 = capfd.readouterr().err.count("[ndfb] four-step")
+        hs.run("ndfft", 1024, (20, 1024), 1, np.float32, seed=3)         # contiguous rows: 8 KB each -> groups of 8 rows
+        n3 = capfd.readouterr().err.count("[ndfb] four-step")
+        hs.run("ndfft", 64, (3, 64, 130), 1, np.float64, seed=4)         # outer dim to single indices, then column groups
+        n4 = capfd.readouterr().err.count("[ndfb] four-step")
+        hs.run("ndfft", 16384, (2, 16384), 1, np.float64, seed=5)        # one lane is bigger than a group: not sliced
+        n5 = capfd.readouterr().err.count("[ndfb] four-step")
+    finally:
+        for k in ("NDFB_FORCE_FOUR_STEP", "NDFB_FS_L2_KB", "NDFB_TRACE"):
+            del os.environ[k]
+    assert (n1, n2, n3, n4, n5) == (2, 3, 3, 9, 1), (n1, n2, n3, n4, n5)

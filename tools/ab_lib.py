@@ -44,6 +44,10 @@ CASES = [  # name, fn, in shape, out shape, axis, dtype, n, handler
     ("c5a 384 axis2", "ndfft", (360, 1000, 384), None, 2, np.float64, 384, "FftHandler"),
     ("rows 1024 f32", "ndfft", (65536, 1024), None, 1, np.float32, 1024, "FftHandler"),
     ("rows 4096 f64", "ndfft", (8192, 4096), None, 1, np.float64, 4096, "FftHandler"),
+    ("rows 2048 f32", "ndfft", (32768, 2048), None, 1, np.float32, 2048, "FftHandler"),
+    ("rows 1024 f64", "ndfft", (32768, 1024), None, 1, np.float64, 1024, "FftHandler"),
+    ("cols 2048 f64", "ndfft", (2048, 16384), None, 0, np.float64, 2048, "FftHandler"),
+    ("cols 512 f32", "ndfft", (512, 131072), None, 0, np.float32, 512, "FftHandler"),
     ("blu 1009 f32 rows", "ndfft", (33216, 1009), None, 1, np.float32, 1009, "FftHandler"),
 ]
 
