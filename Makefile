@@ -2,7 +2,7 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 CSRC      := ndrustfft_b200/csrc
-SRCS      := $(CSRC)/ndfft_b200.cu $(sort $(wildcard $(CSRC)/sfft_inst_*.cu) $(wildcard $(CSRC)/rsfft_inst_*.cu) $(wildcard $(CSRC)/bsfft_inst_*.cu))
+SRCS      := $(CSRC)/ndfft_b200.cu $(sort $(wildcard $(CSRC)/sfft_inst_*.cu) $(wildcard $(CSRC)/rsfft_inst_*.cu) $(wildcard $(CSRC)/bsfft_inst_*.cu) $(wildcard $(CSRC)/fs2_inst*.cu))
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh $(CSRC)/*.inc) include/ndfft_b200.h
 LIBDIR    := ndrustfft_b200/lib
 LIB       := $(LIBDIR)/libndfft_b200.so

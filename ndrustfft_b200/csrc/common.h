@@ -78,6 +78,20 @@ NDFB_DEV double ld_stream(const double* p) {
 }
 #endif
 
+// L2-coherent load (bypasses the non-coherent L1): for data written by other CTAs of the same launch
+#ifdef NDFB_EMU
+template <typename T> NDFB_DEV T ld_cg(const T* p) { return *p; }
+#else
+NDFB_DEV Cx<float> ld_cg(const Cx<float>* p) {
+    float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+    return cmake<float>(v.x, v.y);
+}
+NDFB_DEV Cx<double> ld_cg(const Cx<double>* p) {
+    double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return cmake<double>(v.x, v.y);
+}
+#endif
+
 // What one launch of the tile kernel computes around its forward complex FFT core of length N.
 // (n = the handler's logical length; see DESIGN.md "kinds" for the algebra, verified in tests/kernel_math_model.py.)
 enum TileKind : int {

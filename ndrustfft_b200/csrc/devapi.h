@@ -44,6 +44,7 @@ inline void dev_free(void* p) { std::free(p); }
 inline int dev_h2d(void* d, const void* h, size_t bytes, stream_t) { std::memcpy(d, h, bytes); return 0; }
 inline int dev_d2h(void* h, const void* d, size_t bytes, stream_t) { std::memcpy(h, d, bytes); return 0; }
 inline int dev_sync(stream_t) { return 0; }
+inline int dev_memset0(void* d, size_t bytes, stream_t) { std::memset(d, 0, bytes); return 0; }
 inline size_t dev_smem_cap(int) { return 227 * 1024; }
 inline int dev_sm_count(int) { return 148; }
 template <typename K, typename A>
@@ -80,6 +81,7 @@ inline void dev_free(void* p) { cudaFree(p); }
 inline int dev_h2d(void* d, const void* h, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); return 0; }
 inline int dev_d2h(void* h, const void* d, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); return 0; }
 inline int dev_sync(stream_t s) { NDFB_CUDA(cudaStreamSynchronize(s)); return 0; }
+inline int dev_memset0(void* d, size_t bytes, stream_t s) { NDFB_CUDA(cudaMemsetAsync(d, 0, bytes, s)); return 0; }
 inline size_t dev_smem_cap(int dev) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 227 * 1024; }

@@ -143,6 +143,7 @@ static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
 struct Pool {
     struct Slot { void* p = nullptr; size_t bytes = 0; int device = -1; };
     Slot slots[9];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows, 5: nested four-step workspace,
+                     // 6: tile counters of the fused two-pass kernel,
                      // 7/8: intermediates of ndfb_exec_chain
     ~Pool() {}  // device memory is reclaimed at process exit; explicit release via ndfb_release_workspaces
     int get(int which, int device, size_t bytes, void** out) {
@@ -593,6 +594,77 @@ static bool fits_one_tile(ndfb_plan* p, const CoreTables& t, size_t cs) {
     return (size_t)t.Bl * cs + 64 <= cap;
 }
 
+// Long strided columns, N = N1*N2 <= 2^17: both passes in ONE persistent launch with the workspace ring resident in L2
+// (fs2_kernel).  *done = 0 when the case does not qualify (the caller then runs the two-launch path).
+template <typename R>
+static int exec_fs2(ndfb_plan* p, long long N, bool inverse, double scale, const void* in, void* out, const BDim& cols,
+                    long long is_axis, long long os_axis, stream_t stream, int* done) {
+    *done = 0;
+    if (std::getenv("NDFB_NO_FS2") || N > (1LL << 17)) return 0;
+    const bool f64 = sizeof(R) == 8;
+    // measured on B200 (profiles/r1u_fused_two_pass.jsonl): c64 8192-point columns 0.407 -> 0.383 ms, c128 no gain
+    // (0.400 -> 0.404 ms), so double precision keeps the two-launch path unless asked
+    if (f64 && !std::getenv("NDFB_FS2_F64")) return 0;
+    const size_t cs = sizeof(Cx<R>);
+    const Fs2Entry* e = nullptr;
+    for (int i = 0; i < kFs2_count; ++i)
+        if (kFs2[i].f64 == (f64 ? 1 : 0) && (long long)kFs2[i].N1 * kFs2[i].N2 == N) { e = &kFs2[i]; break; }
+    if (!e) return 0;
+    // group width: the widest divisor of the column count that keeps one group's intermediate within the budget
+    size_t budget = (size_t)8 << 20;
+    if (const char* v = std::getenv("NDFB_FS2_KB")) budget = (size_t)atoll(v) << 10;
+    const long long W0 = cols.size, lm = std::max(e->L1, e->L2);
+    long long Wg = 0;
+    for (long long w = lm; w <= W0; w += lm)
+        if (W0 % w == 0 && (size_t)w * (size_t)N * cs <= budget) Wg = w;
+    if (!Wg) return 0;
+    const long long G = W0 / Wg;
+    if (G < 4 || G > (1 << 20)) return 0;
+    int ring = 3;
+    if (const char* v = std::getenv("NDFB_FS2_RING")) ring = std::max(2, atoi(v));
+    int rc;
+    void *ws = nullptr, *sync = nullptr;
+    if ((rc = g_pool.get(2, p->device, (size_t)ring * (size_t)N * (size_t)Wg * cs, &ws))) return rc;
+    const size_t sync_bytes = (size_t)(2 + 2 * G) * sizeof(unsigned);
+    if ((rc = g_pool.get(6, p->device, sync_bytes, &sync))) return rc;
+    Core* c1 = get_core(p, TK_C2C, e->N1);
+    Core* c2 = get_core(p, TK_C2C, e->N2);
+    if ((rc = ensure_device<R>(p, c1)) || (rc = ensure_device<R>(p, c2))) return rc;
+    ndfb_plan::FsTw fs;
+    if ((rc = get_fs_twiddles<R>(p, N, &fs))) return rc;
+    if (fs.shift < 40) return 0;
+    SfftEntry px1, px2;
+    std::memset(&px1, 0, sizeof px1); std::memset(&px2, 0, sizeof px2);
+    for (int i = 0; i < 4; ++i) { px1.r[i] = e->r1[i]; px2.r[i] = e->r2[i]; }
+    px1.twtotal = e->tw1; px2.twtotal = e->tw2;
+    void *tw1 = nullptr, *tw2 = nullptr;
+    if ((rc = get_sfft_twiddles<R>(p, c1, &px1, &tw1)) || (rc = get_sfft_twiddles<R>(p, c2, &px2, &tw2))) return rc;
+    Fs2Args f;
+    std::memset(&f, 0, sizeof f);
+    f.a1.in = in; f.a1.out = ws; f.a1.is_axis = e->N2 * is_axis; f.a1.os_axis = (long long)e->N2 * Wg;
+    f.a1.conj_in = inverse ? 1 : 0; f.a1.scale = 1.0; f.a1.tw = tw1;
+    f.a1.fs_twiddle = 1; f.a1.fs_shift = fs.shift; f.a1.fs_lo = fs.lo; f.a1.fs_hi = fs.hi;
+    f.a2.in = ws; f.a2.out = out; f.a2.is_axis = Wg; f.a2.os_axis = e->N1 * os_axis;
+    f.a2.conj_out = inverse ? 1 : 0; f.a2.scale = scale; f.a2.tw = tw2;
+    f.sync = (unsigned*)sync;
+    f.G = (int)G; f.Wg = (int)Wg; f.ring = (int)std::min<long long>(ring, G);
+    f.ring_stride = N * Wg;
+    f.col_is = cols.is; f.col_os = cols.os; f.j2_is = is_axis; f.k1_os = os_axis;
+    f.N1 = e->N1; f.N2 = e->N2;
+    if (const char* v = std::getenv("NDFB_FS2_DBG")) f.dbg = atoi(v);
+    f.tiles1 = (unsigned)((Wg / e->L1) * e->N2);
+    f.tiles2 = (unsigned)((Wg / e->L2) * e->N1);
+    const long long total = G * (long long)(f.tiles1 + f.tiles2);
+    if (total > 0x7fffffffLL) return 0;
+    if ((rc = dev_memset0(sync, sync_bytes, stream))) return rc;
+    const long long grid = std::min<long long>(total, (long long)dev_sm_count(p->device) * e->minb);
+    if (std::getenv("NDFB_TRACE"))
+        fprintf(stderr, "[ndfb] fs2 %s N=%lld = %d x %d fused two-pass, %lld groups of %lld columns, ring %d, grid %lld\n", f64 ? "f64" : "f32", N,
+                e->N1, e->N2, G, Wg, f.ring, grid);
+    *done = 1;
+    return e->launch(f, (unsigned)grid, stream);
+}
+
 // C2C of a length too long for one CTA's shared memory: four-step N = N1*N2 through a device workspace.
 template <typename R>
 static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale, const void* in, void* out,
@@ -611,6 +683,11 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     // column pass, a tile at least one 32-byte sector wide), then the most square split
     normalize_dims(dims);
     const bool strided_lanes = !dims.empty() && llabs_(dims[0].is) < llabs_(is_axis) && llabs_(dims[0].os) < llabs_(os_axis);
+    if (depth == 0 && strided_lanes && dims.size() == 1 && conj_in_override < 0 && dims[0].is > 0 && dims[0].os > 0) {
+        int done = 0;
+        int rc = exec_fs2<R>(p, N, inverse, scale, in, out, dims[0], is_axis, os_axis, stream, &done);
+        if (rc || done) return rc;
+    }
     // Optional L2-resident workspace (NDFB_FS_L2_KB=<group size>; off by default): run the two passes group by group over
     // a slice of the lanes and reuse ONE workspace, so that pass 2 reads what pass 1 just wrote from L2 and the two-pass
     // transform costs one HBM round trip.  Measured on B200 (profiles/r1t_l2_groups.jsonl): the DRAM traffic does halve,

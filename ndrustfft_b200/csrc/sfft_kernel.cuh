@@ -229,7 +229,7 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0)
 // ------------------------------------------------------------------------------------------------------
 // MODE 0: plain store;  1: four-step twiddle from the single table W_N^e (N <= 2^17), nothing else;  2: everything
 // (hi/lo twiddle product, split / scattered output blocks).  UNIT: both axis strides are 1 (contiguous rows)
-template <typename R, class S, int L, bool COLS, int MODE, bool UNIT>
+template <typename R, class S, int L, bool COLS, int MODE, bool UNIT, bool CG = false>
 NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, const LaneBase& lb) {
     const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
     Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
@@ -242,7 +242,8 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     const int j2 = lb.j2;
     Cx<R> v[S::E];
     auto load = [&](int j) -> Cx<R> {
-        Cx<R> x = valid ? ld_stream(&in[(long long)j * is_axis]) : cmake<R>((R)0, (R)0);
+        // CG: the array was written by other CTAs of this same launch (fs2_kernel): read it from L2, never from L1
+        Cx<R> x = valid ? (CG ? ld_cg(&in[(long long)j * is_axis]) : ld_stream(&in[(long long)j * is_axis])) : cmake<R>((R)0, (R)0);
         x.y *= sgn_in;
         return x;
     };
@@ -287,6 +288,120 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     else if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb);
     else if (a.fs_twiddle && a.fs_shift >= 40 && !a.os_blk) sfft_body<R, S, L, COLS, 1, false>(a, c, lb);
     else sfft_body<R, S, L, COLS, 2, false>(a, c, lb);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Two-pass (four-step) transform of long STRIDED columns in ONE persistent launch, workspace resident in L2.
+//
+// The columns are cut into groups of Wg adjacent columns.  Pass 1 of group g (N1-point transforms + W_N^{k1 j2} twiddle)
+// writes a small ring buffer; pass 2 of the same group (N2-point transforms) reads it back while it is still in the
+// 126 MB L2 and writes the user's output.  CTAs draw tiles from one ticket counter in the order
+//     P1(0), P1(1), P2(0), P1(2), P2(1), ... , P2(G-1)
+// and a pass-2 tile waits until its group's pass-1 tiles have all signalled (a pass-1 tile waits until the ring slot it
+// overwrites has been consumed).  Every tile a ticket can wait for has a smaller ticket, so the oldest unfinished tile
+// never waits and the launch cannot deadlock, whatever number of CTAs is resident.  HBM sees the input once and the
+// output once; the workspace traffic stays in L2.
+// ------------------------------------------------------------------------------------------------------
+struct Fs2Args {
+    SfftArgs a1, a2;        // pass 1: user input -> ring (four-step twiddle on);  pass 2: ring -> user output
+    unsigned* sync;         // [0] ticket, [1] error flag, [2 + g] pass-1 tiles done, [2 + G + g] pass-2 tiles done
+    int G, Wg, ring;        // groups, columns per group, ring slots
+    long long ring_stride;  // elements per ring slot (N * Wg)
+    long long col_is, col_os;      // column strides of the user's arrays
+    long long j2_is, k1_os;        // user-array strides of the pass-1 lane index j2 and of the pass-2 lane index k1
+    int N1, N2;
+    unsigned tiles1, tiles2;       // tiles per group
+    int dbg;                       // timing experiments only (NDFB_FS2_DBG): 1 = no release fence, 2 = no waits (results invalid)
+};
+
+NDFB_DEV unsigned fs2_ld_acquire(const unsigned* p) {
+#ifdef NDFB_EMU
+    return *p;
+#else
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+
+// thread 0 polls, everybody else waits at the barrier; bounded so that a logic error cannot hang the GPU
+NDFB_DEV void fs2_wait(unsigned* sync, const unsigned* counter, unsigned need) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (fs2_ld_acquire(counter) < need) {
+#ifndef NDFB_EMU
+            __nanosleep(64);
+#endif
+            if (++spins > (1u << 22)) { atomicExch(&sync[1], 1u); break; }
+        }
+    }
+    __syncthreads();
+}
+
+NDFB_DEV void fs2_signal(unsigned* counter, bool fence) {
+    __syncthreads();                  // every thread of the tile has issued its stores (or, for a consumer tile, finished its loads)
+    if (threadIdx.x == 0) {
+        if (fence) __threadfence();   // cumulative: the tile's stores are visible device-wide before the tile is counted
+        atomicAdd(counter, 1u);
+    }
+}
+
+template <typename R, class S1, int L1, class S2, int L2, int MINB>
+__global__ void __launch_bounds__(S1::TL* L1, MINB) fs2_kernel(const __grid_constant__ Fs2Args f) {
+    static_assert(S1::TL * L1 == S2::TL * L2, "both passes run with the same CTA size");
+    NDFB_DYN_SMEM(smem_raw);
+    constexpr size_t kTile1 = sizeof(Cx<R>) * (size_t)L1 * S1::NPAD, kTile2 = sizeof(Cx<R>) * (size_t)L2 * S2::NPAD;
+    unsigned& s_ticket = *reinterpret_cast<unsigned*>(smem_raw + (kTile1 > kTile2 ? kTile1 : kTile2));   // behind the tile buffer
+    const int tid = threadIdx.x;
+    const unsigned per = f.tiles1 + f.tiles2;
+    const unsigned total = (unsigned)f.G * per;
+    for (;;) {
+        __syncthreads();          // the previous tile is done with the shared buffer and with s_ticket
+        if (tid == 0) s_ticket = fs2_ld_acquire(&f.sync[1]) ? 0xffffffffu : atomicAdd(&f.sync[0], 1u);   // (error flag: drain)
+        __syncthreads();
+        const unsigned t = s_ticket;
+        if (t >= total) return;
+        int pass, g;
+        unsigned tile;
+        if (t < f.tiles1) { pass = 0; g = 0; tile = t; }
+        else {
+            const unsigned tt = t - f.tiles1;
+            const int u = 1 + (int)(tt / per);
+            const unsigned r = tt - (unsigned)(u - 1) * per;
+            if (u < f.G && r < f.tiles1) { pass = 0; g = u; tile = r; }
+            else { pass = 1; g = u - 1; tile = u < f.G ? r - f.tiles1 : r; }
+        }
+        const long long slot = (long long)(g % f.ring) * f.ring_stride;
+        if (pass == 0) {
+            if (g >= f.ring && !(f.dbg & 2)) fs2_wait(f.sync, &f.sync[2 + f.G + g - f.ring], f.tiles2);
+            SfftCtx<R, S1, L1, true> c;
+            c.smem = reinterpret_cast<Cx<R>*>(smem_raw);
+            c.l = tid % L1; c.i = tid / L1; c.valid = true;
+            const int cbn = f.Wg / L1;
+            const int cb = (int)(tile % (unsigned)cbn), j2 = (int)(tile / (unsigned)cbn);
+            const int wl = cb * L1 + c.l;
+            LaneBase lb;
+            lb.j2 = j2;
+            lb.bi = (long long)j2 * f.j2_is + ((long long)g * f.Wg + wl) * f.col_is;
+            lb.bo = slot + (long long)j2 * f.Wg + wl;
+            sfft_body<R, S1, L1, true, 1, false>(f.a1, c, lb);
+            fs2_signal(&f.sync[2 + g], !(f.dbg & 1));
+        } else {
+            if (!(f.dbg & 2)) fs2_wait(f.sync, &f.sync[2 + g], f.tiles1);
+            SfftCtx<R, S2, L2, true> c;
+            c.smem = reinterpret_cast<Cx<R>*>(smem_raw);
+            c.l = tid % L2; c.i = tid / L2; c.valid = true;
+            const int cbn = f.Wg / L2;
+            const int cb = (int)(tile % (unsigned)cbn), k1 = (int)(tile / (unsigned)cbn);
+            const int wl = cb * L2 + c.l;
+            LaneBase lb;
+            lb.j2 = 0;
+            lb.bi = slot + (long long)k1 * f.N2 * f.Wg + wl;
+            lb.bo = (long long)k1 * f.k1_os + ((long long)g * f.Wg + wl) * f.col_os;
+            sfft_body<R, S2, L2, true, 0, false, true>(f.a2, c, lb);
+            fs2_signal(&f.sync[2 + f.G + g], false);   // a consumer only reports that it has READ its ring slot
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -194,6 +194,12 @@ using simt::dim3;
 #define __syncwarp(...) ((void)0)
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+// blocks run one after another, fibers of a block are cooperative: plain read-modify-write is atomic here
+template <typename T>
+inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+template <typename T>
+inline T atomicExch(T* p, T v) { T old = *p; *p = v; return old; }
+inline void __threadfence() {}
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int lanemask) {
     return simt::shfl_generic(v, (simt::block()->cur->linear % 32) ^ (unsigned)lanemask);

@@ -508,3 +508,25 @@ def test_four_step_l2_groups(hs, capfd):
         for k in ("NDFB_FORCE_FOUR_STEP", "NDFB_FS_L2_KB", "NDFB_TRACE"):
             del os.environ[k]
     assert (n1, n2, n3, n4, n5) == (2, 3, 3, 9, 1), (n1, n2, n3, n4, n5)
+
+
+def test_fused_two_pass_columns(hs, capfd):
+    """Long strided columns: both four-step passes in one persistent launch over an L2-sized workspace ring (fs2_kernel).
+    NDFB_FS2_KB shrinks the group budget so that small arrays already form >= 4 groups."""
+    import os
+    os.environ.update({"NDFB_TRACE": "1", "NDFB_FS2_KB": "4096", "NDFB_FS2_F64": "1"})
+    try:
+        hs.run("ndfft", 8192, (8192, 256), 0, np.float32, seed=1)                    # 64 x 128, 4 groups of 64 columns
+        hs.run("ndifft", 8192, (8192, 192), 0, np.float64, seed=2, norm="none")      # 6 groups of 32 columns: ring slots reused
+        os.environ["NDFB_FS2_KB"] = "8192"
+        hs.run("ndifft", 16384, (16384, 256), 0, np.float32, seed=3)                 # 128 x 128, 4 groups of 64
+        err = capfd.readouterr().err
+        assert err.count("[ndfb] fs2") == 3 and "four-step" not in err, err
+        hs.run("ndfft", 8192, (8192, 100), 0, np.float32, seed=4)                    # 100 columns: no group width divides -> two launches
+        os.environ["NDFB_NO_FS2"] = "1"
+        hs.run("ndfft", 8192, (8192, 256), 0, np.float32, seed=1)
+        err = capfd.readouterr().err
+        assert "[ndfb] fs2" not in err and err.count("[ndfb] four-step") == 2
+    finally:
+        for k in ("NDFB_TRACE", "NDFB_FS2_KB", "NDFB_NO_FS2", "NDFB_FS2_F64"):
+            os.environ.pop(k, None)

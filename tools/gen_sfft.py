@@ -181,6 +181,22 @@ def bluestein_entries(f64):
     return dedup(out)
 
 
+def fs2_entries():
+    """Fused two-pass kernels (fs2_kernel): N = N1 * N2 strided columns, both passes family-B schedules run by 256-thread CTAs."""
+    out = []
+    for f64 in (0, 1):
+        for N1, N2 in ((64, 128), (128, 128), (128, 256), (256, 256)):
+            TL1, r1 = pow2_schedule(N1, f64, 1)
+            TL2, r2 = pow2_schedule(N2, f64, 1)
+            L1, L2 = 256 // TL1, 256 // TL2
+            r1 = r1 + [1] * (4 - len(r1))
+            r2 = r2 + [1] * (4 - len(r2))
+            R = "double" if f64 else "float"
+            out.append(f"    FS2_ENTRY({R}, {f64}, {N1}, {TL1}, {r1[0]}, {r1[1]}, {r1[2]}, {r1[3]}, {L1}, "
+                       f"{N2}, {TL2}, {r2[0]}, {r2[1]}, {r2[2]}, {r2[3]}, {L2}, 4),")
+    return out
+
+
 def dedup(entries):
     seen, out = set(), []
     for e in entries:
@@ -206,7 +222,7 @@ def write(path, lines):
 
 def main():
     for f in os.listdir(OUT):
-        if f.startswith(("sfft_inst_", "rsfft_inst_", "bsfft_inst_")) and f.endswith(".cu"):
+        if f.startswith(("sfft_inst_", "rsfft_inst_", "bsfft_inst_", "fs2_inst")) and f.endswith(".cu"):
             os.remove(os.path.join(OUT, f))
     total = 0
     head = ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "sfft_inst.h"', "", "namespace ndfb {", ""]
@@ -221,6 +237,9 @@ def main():
         write(f"bsfft_inst_{nm}.cu", head + [f"const BsfftEntry kBsfft_{nm}[] = {{"] + [fmt(e, "BSFFT_ENTRY") for e in ents] +
               ["};", f"const int kBsfft_{nm}_count = {len(ents)};", "", "}  // namespace ndfb"])
         total += len(ents)
+    ents = fs2_entries()
+    write("fs2_inst.cu", head + ["const Fs2Entry kFs2[] = {"] + ents + ["};", f"const int kFs2_count = {len(ents)};", "", "}  // namespace ndfb"])
+    total += len(ents)
     rnames = []
     for f64 in (0, 1):
         ents = real_entries(f64)
