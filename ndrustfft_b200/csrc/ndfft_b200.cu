@@ -145,8 +145,42 @@ struct Pool {
     Slot slots[9];   // 0/1: host staging in/out, 2: four-step workspace, 3/4: staged-path rows, 5: nested four-step workspace,
                      // 6: tile counters of the fused two-pass kernel,
                      // 7/8: intermediates of ndfb_exec_chain
+    // The workspaces belong to the host thread, not to a stream.  A call on stream B right after a call on stream A
+    // would reuse a workspace A's kernels may still be using, so each device-memory call that took a workspace records
+    // an event when it is done and the next call on a DIFFERENT stream waits for it first (same stream: stream order).
+    stream_t cur = nullptr, last = nullptr;
+    bool in_call = false, touched = false, have_event = false, waited = false;
+#ifndef NDFB_EMU
+    cudaEvent_t ev = nullptr;
+#endif
     ~Pool() {}  // device memory is reclaimed at process exit; explicit release via ndfb_release_workspaces
+    void begin_call(stream_t s) {
+        cur = s; in_call = true; touched = false; waited = false;
+#ifndef NDFB_EMU
+        // inside a stream capture the caller owns the ordering (an event from outside may not be waited on there)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) cudaGetLastError();
+        if (cs != cudaStreamCaptureStatusNone) in_call = false;
+#endif
+    }
+    void end_call() {
+#ifndef NDFB_EMU
+        if (in_call && touched) {
+            if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; cudaGetLastError(); }
+            if (ev && cudaEventRecord(ev, cur) == cudaSuccess) { have_event = true; last = cur; }
+            else { cudaGetLastError(); have_event = false; }
+        }
+#endif
+        in_call = false;
+    }
     int get(int which, int device, size_t bytes, void** out) {
+#ifndef NDFB_EMU
+        if (in_call && !waited && have_event && last != cur) {
+            if (cudaStreamWaitEvent(cur, ev, 0) != cudaSuccess) { cudaGetLastError(); cudaDeviceSynchronize(); }
+            waited = true;
+        }
+#endif
+        touched = true;
         Slot& s = slots[which];
         if (s.p && (s.bytes < bytes || s.device != device)) { dev_free(s.p); s.p = nullptr; s.bytes = 0; }
         if (!s.p) {
@@ -160,6 +194,7 @@ struct Pool {
     }
     void release() {
         for (auto& s : slots) { if (s.p) dev_free(s.p); s.p = nullptr; s.bytes = 0; }
+        have_event = false;
     }
 };
 static thread_local Pool g_pool;
@@ -1222,8 +1257,12 @@ static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const voi
                     const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
                     const ptrdiff_t* strides_out, int axis, int mem, void* stream_v) {
     stream_t stream = (stream_t)stream_v;
-    if (mem == NDFB_MEM_DEVICE)
-        return exec_device<R>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, stream);
+    if (mem == NDFB_MEM_DEVICE) {
+        g_pool.begin_call(stream);
+        const int rc = exec_device<R>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, stream);
+        g_pool.end_call();
+        return rc;
+    }
     // host arrays: move the touched byte spans through device staging buffers, strides unchanged
     const size_t ie = (o.in_complex ? 2 : 1) * sizeof(R), oe = (o.out_complex ? 2 : 1) * sizeof(R);
     long long ilo, ihi, olo, ohi;
@@ -1415,7 +1454,10 @@ static int chain_any(const std::vector<ChainStep>& st, const void* in, void* out
     vo.shape.assign(shape_out, shape_out + ndim); vo.strides.assign(strides_out, strides_out + ndim); vo.where = 1;
     if (mem == NDFB_MEM_DEVICE) {
         vi.ptr = const_cast<void*>(in); vo.ptr = out;
-        return chain_device<R>(st, vi, vo, stream);
+        g_pool.begin_call(stream);
+        rc = chain_device<R>(st, vi, vo, stream);
+        g_pool.end_call();
+        return rc;
     }
     const size_t ie = (st.front().o.in_complex ? 2 : 1) * sizeof(R), oe = (st.back().o.out_complex ? 2 : 1) * sizeof(R);
     long long ilo, ihi, olo, ohi;

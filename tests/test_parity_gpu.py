@@ -491,3 +491,60 @@ def test_single_call_in_place_device(dev, op, n, shape, axis):
     buf = x.clone()
     getattr(be, op)(buf, buf, h, axis)
     assert torch.equal(buf, want)
+
+
+def test_fused_two_pass_columns_device(dev):
+    # c2 axis 0 runs both column passes in one persistent launch (fs2_kernel); same bits as the two-launch path
+    import os
+    be = dev.be
+    x = _rand((8192, 1024), np.float32, True, 21)
+    h = be.FftHandler(8192, np.float32)
+    y = torch.empty_like(x); y2 = torch.empty_like(x)
+    l0 = be.lib.launch_count()
+    be.ndfft(x, y, h, 0)
+    assert be.lib.launch_count() - l0 == 1
+    os.environ["NDFB_NO_FS2"] = "1"
+    try:
+        l0 = be.lib.launch_count()
+        be.ndfft(x, y2, h, 0)
+        assert be.lib.launch_count() - l0 == 2
+    finally:
+        del os.environ["NDFB_NO_FS2"]
+    assert torch.equal(y, y2)
+    _lane_subset_check(be, "ndfft", 8192, x, y, 0, np.float32, nsample=16)
+    # inverse, in place, and a column count that is not a power of two (groups of 192 = 3 x 64 columns)
+    xi = _rand((8192, 960), np.float32, True, 22)
+    buf = xi.clone()
+    be.ndfft(buf, buf, h, 0); be.ndifft(buf, buf, h, 0)
+    assert _rel(buf, xi) < 1e-5
+    # double precision on request
+    os.environ["NDFB_FS2_F64"] = "1"
+    try:
+        xd = _rand((8192, 512), np.float64, True, 23)
+        hd = be.FftHandler(8192, np.float64)
+        yd = torch.empty_like(xd)
+        l0 = be.lib.launch_count()
+        be.ndfft(xd, yd, hd, 0)
+        assert be.lib.launch_count() - l0 == 1
+        _lane_subset_check(be, "ndfft", 8192, xd, yd, 0, np.float64, nsample=16)
+    finally:
+        del os.environ["NDFB_FS2_F64"]
+
+
+def test_workspace_reuse_across_streams(dev):
+    # two-pass transforms from one host thread on two streams share the thread's workspace: the library orders them
+    be = dev.be
+    h = be.FftHandler(1 << 16, np.float32)
+    x1 = _rand((64, 1 << 16), np.float32, True, 31); x2 = _rand((64, 1 << 16), np.float32, True, 32)
+    w1 = torch.empty_like(x1); w2 = torch.empty_like(x2)
+    be.ndfft(x1, w1, h, 1); be.ndfft(x2, w2, h, 1)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    y1 = torch.empty_like(x1); y2 = torch.empty_like(x2)
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            be.ndfft(x1, y1, h, 1)
+        with torch.cuda.stream(s2):
+            be.ndfft(x2, y2, h, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, w1) and torch.equal(y2, w2)
