@@ -640,10 +640,13 @@ static int exec_fs2(ndfb_plan* p, long long N, bool inverse, double scale, const
     // measured on B200 (profiles/r1u_fused_two_pass.jsonl): c64 8192-point columns 0.407 -> 0.383 ms, c128 no gain
     // (0.400 -> 0.404 ms), so double precision keeps the two-launch path unless asked
     if (f64 && !std::getenv("NDFB_FS2_F64")) return 0;
+    // longer columns (128 x 128, 256 x 256) measured slower fused than as two launches (0.40 vs 0.38 ms, 0.45 vs 0.42 ms)
+    if (N != 8192 && !std::getenv("NDFB_FS2_ALL")) return 0;
     const size_t cs = sizeof(Cx<R>);
     const Fs2Entry* e = nullptr;
+    const int want_t = std::getenv("NDFB_FS2_T") ? atoi(std::getenv("NDFB_FS2_T")) : 0;
     for (int i = 0; i < kFs2_count; ++i)
-        if (kFs2[i].f64 == (f64 ? 1 : 0) && (long long)kFs2[i].N1 * kFs2[i].N2 == N) { e = &kFs2[i]; break; }
+        if (kFs2[i].f64 == (f64 ? 1 : 0) && (long long)kFs2[i].N1 * kFs2[i].N2 == N && (!want_t || kFs2[i].threads == want_t)) { e = &kFs2[i]; break; }
     if (!e) return 0;
     // group width: the widest divisor of the column count that keeps one group's intermediate within the budget
     size_t budget = (size_t)8 << 20;

@@ -91,6 +91,45 @@ struct SfftCtx {
 // Pass 0 takes its inputs from `load(j)` (global memory, coalesced in b), the last pass hands its outputs to
 // `store(k, value)`.  SYNC0 / SYNCL add a barrier after the loads of the first / last pass for callers whose
 // load or store functor itself goes through the shared buffer (staged rows, pair epilogues).
+// Load / store functors may offer a CURSOR interface (member kStrided): the r inputs / outputs of one butterfly are
+// NB points apart, so the functor walks a pointer by a precomputed step instead of forming j * stride (a 64-bit multiply
+// plus scaling per access: a third of the instructions of the strided-column kernels before; profiles/r1v opmix).
+template <class F, class = void> struct sfft_is_strided { static constexpr bool value = false; };
+template <class F> struct sfft_is_strided<F, decltype((void)F::kStrided)> { static constexpr bool value = true; };
+
+// strided complex array in global memory (sfft_body, MODE 0 / 1)
+template <typename R, bool CG>
+struct SfftGLoad {
+    static constexpr bool kStrided = true;
+    const Cx<R>* in; long long is_axis; R sgn; bool valid;
+    struct Cur { const Cx<R>* p; long long step; };
+    NDFB_DEV Cur start(int b, int nb) const { Cur u; u.p = in + (long long)b * is_axis; u.step = (long long)nb * is_axis; return u; }
+    NDFB_DEV Cx<R> next(Cur& u) const {
+        // CG: the array was written by other CTAs of this same launch (fs2_kernel): read it from L2, never from L1
+        Cx<R> x = valid ? (CG ? ld_cg(u.p) : ld_stream(u.p)) : cmake<R>((R)0, (R)0);
+        u.p += u.step;
+        x.y *= sgn;
+        return x;
+    }
+};
+template <typename R, int MODE>
+struct SfftGStore {
+    static constexpr bool kStrided = true;
+    Cx<R>* out; long long os_axis; R sc, sy; bool valid; const Cx<R>* fs; unsigned j2;
+    struct Cur { Cx<R>* p; long long step; const Cx<R>* t; unsigned tstep; };
+    NDFB_DEV Cur start(int b, int nb) const {
+        Cur u; u.p = out + (long long)b * os_axis; u.step = (long long)nb * os_axis;
+        u.t = fs + (unsigned)b * j2; u.tstep = (unsigned)nb * j2;
+        return u;
+    }
+    NDFB_DEV void next(Cur& u, Cx<R> val) const {
+        Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
+        if (MODE == 1) { y = cmul(y, ldg(u.t)); u.t += u.tstep; }   // four-step twiddle W_N^{k j2}, k = b + q nb
+        if (valid) *u.p = y;
+        u.p += u.step;
+    }
+};
+
 template <typename R, class S, int L, bool COLS, int PASS, bool SYNC0, bool SYNCL>
 struct SfftPass {
     static constexpr int r = S::radix(PASS);
@@ -114,11 +153,17 @@ struct SfftPass {
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
             if (FULL || b < NB) {
+                if constexpr (FIRST && sfft_is_strided<LoadF>::value) {
+                    auto cur = load.start(b, NB);
 #pragma unroll
-                for (int q = 0; q < r; ++q) {
-                    if (FIRST) v[m * r + q] = load(b + q * NB);
-                    else if (FR) v[m * r + q] = c.smem[rbase + S::pad(S::TL * m + q * NB) * c.kscale];
-                    else v[m * r + q] = c.smem[c.addr(b + q * NB)];
+                    for (int q = 0; q < r; ++q) v[m * r + q] = load.next(cur);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < r; ++q) {
+                        if constexpr (FIRST) v[m * r + q] = load(b + q * NB);
+                        else if (FR) v[m * r + q] = c.smem[rbase + S::pad(S::TL * m + q * NB) * c.kscale];
+                        else v[m * r + q] = c.smem[c.addr(b + q * NB)];
+                    }
                 }
             }
         }
@@ -154,7 +199,11 @@ struct SfftPass {
                     }
                 }
                 Dft<R, r>::run(&v[m * r]);
-                if (LAST) {
+                if constexpr (LAST && sfft_is_strided<StoreF>::value) {
+                    auto cur = store.start(b, NB);
+#pragma unroll
+                    for (int q = 0; q < r; ++q) store.next(cur, v[m * r + q]);
+                } else if constexpr (LAST) {
 #pragma unroll
                     for (int q = 0; q < r; ++q) store(b + q * NB, v[m * r + q]);   // (b-k) r + k + q P with P = N/r, k = b
                 } else if (FW) {
@@ -241,6 +290,13 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     const bool valid = c.valid;
     const int j2 = lb.j2;
     Cx<R> v[S::E];
+    if constexpr (MODE != 2) {
+        SfftGLoad<R, CG> gl; gl.in = in; gl.is_axis = is_axis; gl.sgn = sgn_in; gl.valid = valid;
+        SfftGStore<R, MODE> gs; gs.out = out; gs.os_axis = os_axis; gs.sc = sc; gs.sy = sy; gs.valid = valid;
+        gs.fs = reinterpret_cast<const Cx<R>*>(a.fs_lo); gs.j2 = (unsigned)j2;
+        SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, gl, gs);
+        return;
+    }
     auto load = [&](int j) -> Cx<R> {
         // CG: the array was written by other CTAs of this same launch (fs2_kernel): read it from L2, never from L1
         Cx<R> x = valid ? (CG ? ld_cg(&in[(long long)j * is_axis]) : ld_stream(&in[(long long)j * is_axis])) : cmake<R>((R)0, (R)0);
@@ -324,25 +380,28 @@ NDFB_DEV unsigned fs2_ld_acquire(const unsigned* p) {
 #endif
 }
 
-// thread 0 polls, everybody else waits at the barrier; bounded so that a logic error cannot hang the GPU
-NDFB_DEV void fs2_wait(unsigned* sync, const unsigned* counter, unsigned need) {
-    if (threadIdx.x == 0) {
-        unsigned spins = 0;
-        while (fs2_ld_acquire(counter) < need) {
-#ifndef NDFB_EMU
-            __nanosleep(64);
-#endif
-            if (++spins > (1u << 22)) { atomicExch(&sync[1], 1u); break; }
-        }
-    }
-    __syncthreads();
+// ticket -> (pass, group, tile) in the order P1(0), P1(1), P2(0), P1(2), P2(1), ..., P2(G-1)
+struct Fs2Tile { int pass, g; unsigned tile; };
+NDFB_DEV Fs2Tile fs2_decode(const Fs2Args& f, unsigned t) {
+    Fs2Tile o;
+    const unsigned per = f.tiles1 + f.tiles2;
+    if (t < f.tiles1) { o.pass = 0; o.g = 0; o.tile = t; return o; }
+    const unsigned tt = t - f.tiles1;
+    const int u = 1 + (int)(tt / per);
+    const unsigned r = tt - (unsigned)(u - 1) * per;
+    if (u < f.G && r < f.tiles1) { o.pass = 0; o.g = u; o.tile = r; }
+    else { o.pass = 1; o.g = u - 1; o.tile = u < f.G ? r - f.tiles1 : r; }
+    return o;
 }
 
-NDFB_DEV void fs2_signal(unsigned* counter, bool fence) {
-    __syncthreads();                  // every thread of the tile has issued its stores (or, for a consumer tile, finished its loads)
-    if (threadIdx.x == 0) {
-        if (fence) __threadfence();   // cumulative: the tile's stores are visible device-wide before the tile is counted
-        atomicAdd(counter, 1u);
+// bounded poll (thread 0 only), so that a logic error cannot hang the GPU: it raises the error flag instead
+NDFB_DEV void fs2_poll(unsigned* sync, const unsigned* counter, unsigned need) {
+    unsigned spins = 0;
+    while (fs2_ld_acquire(counter) < need) {
+#ifndef NDFB_EMU
+        __nanosleep(64);
+#endif
+        if (++spins > (1u << 22)) { atomicExch(&sync[1], 1u); break; }
     }
 }
 
@@ -353,53 +412,58 @@ __global__ void __launch_bounds__(S1::TL* L1, MINB) fs2_kernel(const __grid_cons
     constexpr size_t kTile1 = sizeof(Cx<R>) * (size_t)L1 * S1::NPAD, kTile2 = sizeof(Cx<R>) * (size_t)L2 * S2::NPAD;
     unsigned& s_ticket = *reinterpret_cast<unsigned*>(smem_raw + (kTile1 > kTile2 ? kTile1 : kTile2));   // behind the tile buffer
     const int tid = threadIdx.x;
-    const unsigned per = f.tiles1 + f.tiles2;
-    const unsigned total = (unsigned)f.G * per;
+    const unsigned total = (unsigned)f.G * (f.tiles1 + f.tiles2);
+    unsigned* pending = nullptr;   // (thread 0) counter of the tile this CTA has just finished
+    bool pending_fence = false;
     for (;;) {
-        __syncthreads();          // the previous tile is done with the shared buffer and with s_ticket
-        if (tid == 0) s_ticket = fs2_ld_acquire(&f.sync[1]) ? 0xffffffffu : atomicAdd(&f.sync[0], 1u);   // (error flag: drain)
+        __syncthreads();           // every thread has issued the previous tile's stores and is done with the shared buffer
+        if (tid == 0) {
+            if (pending) {
+                if (pending_fence) __threadfence();   // cumulative over the CTA's stores (ordered before by the barrier)
+                atomicAdd(pending, 1u);
+            }
+            const unsigned t = fs2_ld_acquire(&f.sync[1]) ? 0xffffffffu : atomicAdd(&f.sync[0], 1u);   // (error flag: drain)
+            s_ticket = t;
+            if (t < total && !(f.dbg & 2)) {
+                const Fs2Tile w = fs2_decode(f, t);
+                if (w.pass == 0) { if (w.g >= f.ring) fs2_poll(f.sync, &f.sync[2 + f.G + w.g - f.ring], f.tiles2); }   // ring slot consumed
+                else fs2_poll(f.sync, &f.sync[2 + w.g], f.tiles1);                                                     // group produced
+            }
+        }
         __syncthreads();
         const unsigned t = s_ticket;
         if (t >= total) return;
-        int pass, g;
-        unsigned tile;
-        if (t < f.tiles1) { pass = 0; g = 0; tile = t; }
-        else {
-            const unsigned tt = t - f.tiles1;
-            const int u = 1 + (int)(tt / per);
-            const unsigned r = tt - (unsigned)(u - 1) * per;
-            if (u < f.G && r < f.tiles1) { pass = 0; g = u; tile = r; }
-            else { pass = 1; g = u - 1; tile = u < f.G ? r - f.tiles1 : r; }
-        }
+        const Fs2Tile w = fs2_decode(f, t);
+        const int g = w.g;
         const long long slot = (long long)(g % f.ring) * f.ring_stride;
-        if (pass == 0) {
-            if (g >= f.ring && !(f.dbg & 2)) fs2_wait(f.sync, &f.sync[2 + f.G + g - f.ring], f.tiles2);
+        if (w.pass == 0) {
             SfftCtx<R, S1, L1, true> c;
             c.smem = reinterpret_cast<Cx<R>*>(smem_raw);
             c.l = tid % L1; c.i = tid / L1; c.valid = true;
             const int cbn = f.Wg / L1;
-            const int cb = (int)(tile % (unsigned)cbn), j2 = (int)(tile / (unsigned)cbn);
+            const int cb = (int)(w.tile % (unsigned)cbn), j2 = (int)(w.tile / (unsigned)cbn);
             const int wl = cb * L1 + c.l;
             LaneBase lb;
             lb.j2 = j2;
             lb.bi = (long long)j2 * f.j2_is + ((long long)g * f.Wg + wl) * f.col_is;
             lb.bo = slot + (long long)j2 * f.Wg + wl;
             sfft_body<R, S1, L1, true, 1, false>(f.a1, c, lb);
-            fs2_signal(&f.sync[2 + g], !(f.dbg & 1));
+            pending = &f.sync[2 + g];
+            pending_fence = !(f.dbg & 1);
         } else {
-            if (!(f.dbg & 2)) fs2_wait(f.sync, &f.sync[2 + g], f.tiles1);
             SfftCtx<R, S2, L2, true> c;
             c.smem = reinterpret_cast<Cx<R>*>(smem_raw);
             c.l = tid % L2; c.i = tid / L2; c.valid = true;
             const int cbn = f.Wg / L2;
-            const int cb = (int)(tile % (unsigned)cbn), k1 = (int)(tile / (unsigned)cbn);
+            const int cb = (int)(w.tile % (unsigned)cbn), k1 = (int)(w.tile / (unsigned)cbn);
             const int wl = cb * L2 + c.l;
             LaneBase lb;
             lb.j2 = 0;
             lb.bi = slot + (long long)k1 * f.N2 * f.Wg + wl;
             lb.bo = (long long)k1 * f.k1_os + ((long long)g * f.Wg + wl) * f.col_os;
             sfft_body<R, S2, L2, true, 0, false, true>(f.a2, c, lb);
-            fs2_signal(&f.sync[2 + f.G + g], false);   // a consumer only reports that it has READ its ring slot
+            pending = &f.sync[2 + f.G + g];
+            pending_fence = false;   // a consumer only reports that it has READ its ring slot
         }
     }
 }

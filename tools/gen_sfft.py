@@ -188,12 +188,15 @@ def fs2_entries():
         for N1, N2 in ((64, 128), (128, 128), (128, 256), (256, 256)):
             TL1, r1 = pow2_schedule(N1, f64, 1)
             TL2, r2 = pow2_schedule(N2, f64, 1)
-            L1, L2 = 256 // TL1, 256 // TL2
             r1 = r1 + [1] * (4 - len(r1))
             r2 = r2 + [1] * (4 - len(r2))
             R = "double" if f64 else "float"
-            out.append(f"    FS2_ENTRY({R}, {f64}, {N1}, {TL1}, {r1[0]}, {r1[1]}, {r1[2]}, {r1[3]}, {L1}, "
-                       f"{N2}, {TL2}, {r2[0]}, {r2[1]}, {r2[2]}, {r2[3]}, {L2}, 4),")
+            for T in (256, 128):          # first match is the default; NDFB_FS2_T picks the other
+                L1, L2 = T // TL1, T // TL2
+                if min(L1, L2) * (16 if f64 else 8) < 64:
+                    continue
+                out.append(f"    FS2_ENTRY({R}, {f64}, {N1}, {TL1}, {r1[0]}, {r1[1]}, {r1[2]}, {r1[3]}, {L1}, "
+                           f"{N2}, {TL2}, {r2[0]}, {r2[1]}, {r2[2]}, {r2[3]}, {L2}, {1024 // T}),")
     return out
 
 

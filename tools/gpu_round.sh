@@ -11,7 +11,7 @@ fi
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
 timeout 900 python tools/bench_configs.py ${SWEEP_ARGS} > gpurun_out/configs_$TAG.jsonl 2> gpurun_out/configs.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sfft_kernel|tile_kernel' -s 4 -c 4 -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fs2_kernel|sfft_kernel|tile_kernel' -s 4 -c 4 -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 if [ -n "$EXTRA_NCU" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rsfft_kernel|sfft_kernel' -c 14 -o gpurun_out/prof_${TAG}_sweep python tools/bench_configs.py --only c3,c4 --iters 1 > gpurun_out/ncu_sweep.log 2>&1
 fi
