@@ -247,13 +247,16 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0)
 #pragma unroll
             for (int d = 0; d < kMaxBatchDims; ++d) {
                 if (d < a.nbd) {
-                    const unsigned sz = (unsigned)a.bsz[d];
-                    const unsigned q = g32 / sz;
-                    const unsigned rr = g32 - q * sz;
+                    unsigned rr = g32;                 // the slowest dim takes what is left: no division (g < nlanes)
+                    if (d + 1 < a.nbd) {
+                        const unsigned sz = (unsigned)a.bsz[d];
+                        const unsigned q = g32 / sz;
+                        rr = g32 - q * sz;
+                        g32 = q;
+                    }
                     if (d == fs_dim) o.j2 = (int)rr;
                     o.bi += (long long)rr * a.bis[d];
                     o.bo += (long long)rr * a.bos[d];
-                    g32 = q;
                 }
             }
         } else {
@@ -552,9 +555,11 @@ struct RsfftArgs {
     const void* tabB; // DCT-II/III: exp(-i pi k / (2n));  DCT-IV: exp(-i pi (4j+1) / (4n))
 };
 
-template <typename R, class S, int L, bool COLS, int KIND, int MINB>
-__global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_constant__ RsfftArgs a) {
+// UNIT: contiguous rows on both sides (axis strides 1): address arithmetic folds to constants
+template <typename R, class S, int L, bool COLS, int KIND, bool UNIT>
+NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     constexpr int N = S::N;
+    constexpr int n = KIND == RK_DCT1 ? N + 1 : 2 * N;   // logical real length (== a.n; the host only launches matching plans)
     constexpr bool IN_CX = KIND == RK_C2R;
     constexpr bool OUT_CX = KIND == RK_R2C;
     // which sides need the coalesced staging copy when the lane is a contiguous row
@@ -576,11 +581,10 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
     const Cx<R>* __restrict__ in_c = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
     R* __restrict__ out_r = reinterpret_cast<R*>(a.out) + (OUT_CX ? 2 * lb.bo : lb.bo);
     Cx<R>* __restrict__ out_c = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
-    const long long is_axis = a.is_axis, os_axis = a.os_axis;
+    const long long is_axis = UNIT ? 1 : a.is_axis, os_axis = UNIT ? 1 : a.os_axis;
     const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
     const Cx<R>* __restrict__ tabA = reinterpret_cast<const Cx<R>*>(a.tabA);
     const Cx<R>* __restrict__ tabB = reinterpret_cast<const Cx<R>*>(a.tabB);
-    const int n = a.n;
     const R sc = (R)a.scale;
     const R zero = (R)0;
     // staged real lane in shared memory (rows only): real index t of lane l
@@ -593,7 +597,12 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
     if (STAGE_IN) {
         // coalesced global read; the kind's reorder is applied on the shared-memory side so that the first pass reads
         // plain complex slots (conflict free):  DCT-II: Makhoul order v[p(t)];  DCT-IV: u[j] = (x[2j], x[n-1-2j])
-        for (int t = c.i; t < n; t += S::TL) {
+        // (compile-time trip count: the copies unroll and all of a thread's loads are in flight together)
+        constexpr int IT = (n + S::TL - 1) / S::TL;
+#pragma unroll
+        for (int m = 0; m < IT; ++m) {
+            const int t = c.i + m * S::TL;
+            if (n % S::TL != 0 && t >= n) break;
             const int pos = KIND == RK_DCT2 ? ((t & 1) ? n - 1 - (t >> 1) : (t >> 1)) : ((t & 1) ? n - t : t);
             sreal(pos) = valid ? ld_stream(&in_r[(long long)t * is_axis]) : zero;
         }
@@ -674,34 +683,63 @@ __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_cons
 
     if (PAIR_EPI) {
         __syncthreads();
-        // bins 0..N of the length-2N real DFT from the packed N-point result
-        for (int k = c.i; k <= N; k += S::TL) {
-            const Cx<R> zk = c.smem[c.addr(k == N ? 0 : k)];
-            const Cx<R> zc = cconj(c.smem[c.addr(k == 0 ? 0 : N - k)]);
+        // bins 0..N of the length-2N real DFT from the packed N-point result.  Bins k and N-k need the same two slots
+        // Z[k], Z[N-k] and conjugate-related factors (tabA[N-k] = -conj(tabA[k])), so one thread produces both: with
+        // s = Z[k] + conj(Z[N-k]), d = w (Z[k] - conj(Z[N-k])):  X[k] = (s - i d)/2,  X[N-k] = (conj(s) - i conj(d))/2.
+        // (k = 0 pairs with N, both from Z[0]; k = N/2 pairs with itself.)
+        constexpr int ITP = (N / 2 + 1 + S::TL - 1) / S::TL;
+#pragma unroll
+        for (int m = 0; m < ITP; ++m) {
+            const int k = c.i + m * S::TL;
+            if (k > N / 2) break;
+            const int k2 = N - k;
+            const Cx<R> zk = c.smem[c.addr(k)];
+            const Cx<R> zc = cconj(c.smem[c.addr(k == 0 ? 0 : k2)]);
             const Cx<R> w = ldg(&tabA[k]);
             const Cx<R> s = cadd(zk, zc), d = cmul(w, csub(zk, zc));
             const Cx<R> X = cmake<R>((R)0.5 * (s.x + d.y), (R)0.5 * (s.y - d.x));
+            const Cx<R> X2 = cmake<R>((R)0.5 * (s.x - d.y), (R)-0.5 * (s.y + d.x));
             if (!valid) continue;
+            const bool two = k2 != k;
             if (KIND == RK_R2C) {
                 out_c[(long long)k * os_axis] = cmake<R>(sc * X.x, sc * X.y);
+                if (two) out_c[(long long)k2 * os_axis] = cmake<R>(sc * X2.x, sc * X2.y);
             } else if (KIND == RK_DCT1) {
                 out_r[(long long)k * os_axis] = (R)0.5 * sc * X.x;
+                if (two) out_r[(long long)k2 * os_axis] = (R)0.5 * sc * X2.x;
             } else {  // RK_DCT2
                 const Cx<R> A = cmul(X, ldg(&tabB[k]));
                 out_r[(long long)k * os_axis] = sc * A.x;
-                if (k > 0 && k < N) out_r[(long long)(n - k) * os_axis] = -sc * A.y;
+                if (k > 0) out_r[(long long)(n - k) * os_axis] = -sc * A.y;      // (k <= N/2 < N)
+                if (two) {
+                    const Cx<R> A2 = cmul(X2, ldg(&tabB[k2]));
+                    out_r[(long long)k2 * os_axis] = sc * A2.x;
+                    if (k2 < N) out_r[(long long)(n - k2) * os_axis] = -sc * A2.y;
+                }
             }
         }
     }
     if (STAGE_OUT) {
         __syncthreads();
+        constexpr int ITO = (n + S::TL - 1) / S::TL;
         if (valid)
-            for (int t = c.i; t < n; t += S::TL) {
+#pragma unroll
+            for (int m = 0; m < ITO; ++m) {
+                const int t = c.i + m * S::TL;
+                if (n % S::TL != 0 && t >= n) break;
                 // DCT-III: out[t] = v[p(t)] (inverse Makhoul);  DCT-IV: even t from the real parts, odd t from the imaginary ones
                 const int pos = KIND == RK_DCT3 ? ((t & 1) ? n - 1 - (t >> 1) : (t >> 1)) : ((t & 1) ? n - t : t);
                 out_r[(long long)t * os_axis] = sreal(pos);
             }
     }
+}
+
+template <typename R, class S, int L, bool COLS, int KIND, int MINB>
+__global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_constant__ RsfftArgs a) {
+    if constexpr (!COLS) {
+        if (a.is_axis == 1 && a.os_axis == 1) { rsfft_body<R, S, L, COLS, KIND, true>(a); return; }
+    }
+    rsfft_body<R, S, L, COLS, KIND, false>(a);
 }
 
 }  // namespace ndfb
