@@ -246,6 +246,8 @@ static int resident_threads(const E* e) {
     const int regs = e->f64 ? e->E * 4 + (e->fam == 1 ? 32 : 56) : e->E * 2 + (e->fam == 1 ? 32 : 44);
     int ctas = 65536 / (e->threads * (regs < 32 ? 32 : regs));
     if (e->smem) ctas = std::min<int>(ctas, (int)((227 * 1024) / e->smem));
+    ctas = std::max(ctas, e->minb);     // __launch_bounds__ guarantees at least this many (register-capped variants)
+    if (e->smem) ctas = std::min<int>(ctas, (int)((227 * 1024) / e->smem));
     ctas = std::min(ctas, 2048 / e->threads);
     ctas = std::max(1, std::min(ctas, 32));
     return ctas * e->threads;

@@ -84,6 +84,18 @@ def rows_L(N, TL, r0, cs):
     return p
 
 
+def capped_variants(entries, f64):
+    """Mixed-radix butterflies take ~120 (f64) / ~80 (f32) registers when allowed to; a variant of the same tile capped
+    for twice the CTAs per SM spills 8-16 bytes and runs 1.2-1.5x faster (profiles/r1z_tune_mixed.jsonl): 360-point c128
+    columns 48 % -> 74 % of the roofline.  The host prefers it through the resident-thread rule."""
+    out = []
+    for e in entries:
+        regs_cap = 65536 // (e["T"] * e["minb"] * 2)
+        if e["N"] != 4095 and regs_cap >= (64 if f64 else 48) and e["T"] * e["minb"] * 2 <= 2048:
+            out.append(dict(e, minb=e["minb"] * 2))
+    return out
+
+
 def c2c_rows(f64):
     out = []
     cs = 16 if f64 else 8
@@ -98,6 +110,13 @@ def c2c_rows(f64):
             e = make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam)
             if e["smem"] <= 220 * 1024 and 32 <= e["T"] <= 1024:
                 out.append(e)
+                if N in MIXED:
+                    out.extend(capped_variants([e], f64))
+                elif fam == 1 and N >= 2048 and os.environ.get("NDFB_GEN_EXPERIMENT"):
+                    # one more CTA per SM if shared memory allows it (experiment: NDFB_SFFT_PICK selects it)
+                    mb = e["minb"] + 1
+                    if e["smem"] * mb <= 227 * 1024 and e["T"] * mb <= 2048:
+                        out.append(dict(e, minb=mb))
     return dedup(out)
 
 
@@ -121,6 +140,8 @@ def c2c_cols(f64):
                     continue
                 cand.append(e)
             out.extend(cand[:3])  # the three widest tiles that fit
+            if N in MIXED:
+                out.extend(capped_variants(cand[:2], f64))
     return dedup(out)
 
 
@@ -136,7 +157,12 @@ def real_entries(f64):
             TL, rad = sc
             if TL < 2 or TL > 512:
                 continue
-            out.append(make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam, always_smem=True))
+            e = make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam, always_smem=True)
+            out.append(e)
+            if fam == 1 and N >= 256 and N != 4095 and os.environ.get("NDFB_GEN_EXPERIMENT"):
+                mb = e["minb"] + 1
+                if e["smem"] * mb <= 227 * 1024 and e["T"] * mb <= 2048:
+                    out.append(dict(e, minb=mb))
         for N in [32, 64, 128, 256, 512, 1024, 2048, 4096, 132, 264]:
             sc = schedule(N, f64, fam)
             if sc is None:

@@ -50,6 +50,12 @@ def case(name, fn_name, shape, axis, dt, n, core, nvariants, real=False):
     os.environ.pop(var, None); os.environ.pop("NDFB_STRIDED_FOURSTEP", None)
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "mixed":
+    case("c5a cols 360 f64 axis0", "ndfft", (360, 1000, 384), 0, np.float64, 360, 360, 5)
+    case("c5a cols 1000 f64 axis1", "ndfft", (360, 1000, 384), 1, np.float64, 1000, 1000, 3)
+    case("cols 600 f64", "ndfft", (600, 65536), 0, np.float64, 600, 600, 3)
+    case("cols 384 f64", "ndfft", (384, 131072), 0, np.float64, 384, 384, 5)
+    sys.exit(0)
 case("c3 cols 512 f64 axis1", "ndfft", (512, 512, 257), 1, np.float64, 512, 512, 6)
 case("c3 cols 512 f64 axis0", "ndfft", (512, 512, 257), 0, np.float64, 512, 512, 6)
 case("c5a cols 360 f64 axis0", "ndfft", (360, 1000, 384), 0, np.float64, 360, 360, 3)
