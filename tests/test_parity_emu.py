@@ -530,3 +530,15 @@ def test_fused_two_pass_columns(hs, capfd):
     finally:
         for k in ("NDFB_TRACE", "NDFB_FS2_KB", "NDFB_NO_FS2", "NDFB_FS2_F64", "NDFB_FS2_ALL"):
             os.environ.pop(k, None)
+
+
+def test_dct1_4096_strided_axis_runs_the_4095_point_tile(hs, capfd):
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run("nddct1", 4096, (4096, 5), 0, np.float64, seed=1)
+        hs.run("nddct1", 4096, (4096, 3), 0, np.float32, seed=2, norm="none")
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    assert err.count("[ndfb] rsfft kind=2") == 2 and "N=4095 cols L=2" in err, err

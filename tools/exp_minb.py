@@ -29,16 +29,10 @@ def rnd(shape, rt, cx):
 
 # name, fn, in shape, out shape, axis, dtype, n, handler, env var, core N, (index of the current default, index of the variant)
 CASES = [
-    ("c2 rows 8192 f32", "ndfft", (8192, 8192), None, 1, np.float32, 8192, "FftHandler", "NDFB_SFFT_PICK", 8192, (1, 2)),
-    ("rows 4096 f32", "ndfft", (16384, 4096), None, 1, np.float32, 4096, "FftHandler", "NDFB_SFFT_PICK", 4096, (1, 2)),
-    ("rows 2048 f32", "ndfft", (32768, 2048), None, 1, np.float32, 2048, "FftHandler", "NDFB_SFFT_PICK", 2048, (1, 2)),
-    ("rows 4096 f64", "ndfft", (8192, 4096), None, 1, np.float64, 4096, "FftHandler", "NDFB_SFFT_PICK", 4096, (1, 2)),
-    ("rows 2048 f64", "ndfft", (16384, 2048), None, 1, np.float64, 2048, "FftHandler", "NDFB_SFFT_PICK", 2048, (1, 2)),
-    ("c3 r2c 512 f64 rows", "ndfft_r2c", (512, 512, 512), (512, 512, 257), 2, np.float64, 512, "R2cFftHandler", "NDFB_RSFFT_PICK", 256, (1, 2)),
-    ("c3 c2r 512 f64 rows", "ndifft_r2c", (512, 512, 257), (512, 512, 512), 2, np.float64, 512, "R2cFftHandler", "NDFB_RSFFT_PICK", 256, (1, 2)),
-    ("c4 dct2 rows", "nddct2", (4096, 4096), None, 1, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (1, 2)),
-    ("c4 dct3 rows", "nddct3", (4096, 4096), None, 1, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (1, 2)),
-    ("c4 dct4 rows", "nddct4", (4096, 4096), None, 1, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (1, 2)),
+    ("c4 dct1 rows f64", "nddct1", (4096, 4096), None, 1, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 4095, (0, 1)),
+    ("dct1 4096 rows f32", "nddct1", (8192, 4096), None, 1, np.float32, 4096, "DctHandler", "NDFB_RSFFT_PICK", 4095, (0, 1)),
+    ("c5a rows 384 f64", "ndfft", (360, 1000, 384), None, 2, np.float64, 384, "FftHandler", "NDFB_SFFT_PICK", 384, (0, 1)),
+    ("rows 360 f64", "ndfft", (200000, 360), None, 1, np.float64, 360, "FftHandler", "NDFB_SFFT_PICK", 360, (0, 1)),
 ]
 os.environ["NDFB_TRACE"] = "1"
 for name, fn, si, so, axis, dt, n, hk, var, core, idxs in CASES:

@@ -84,14 +84,14 @@ def rows_L(N, TL, r0, cs):
     return p
 
 
-def capped_variants(entries, f64):
+def capped_variants(entries, f64, allow_4095=False):
     """Mixed-radix butterflies take ~120 (f64) / ~80 (f32) registers when allowed to; a variant of the same tile capped
     for twice the CTAs per SM spills 8-16 bytes and runs 1.2-1.5x faster (profiles/r1z_tune_mixed.jsonl): 360-point c128
     columns 48 % -> 74 % of the roofline.  The host prefers it through the resident-thread rule."""
     out = []
     for e in entries:
         regs_cap = 65536 // (e["T"] * e["minb"] * 2)
-        if e["N"] != 4095 and regs_cap >= (64 if f64 else 48) and e["T"] * e["minb"] * 2 <= 2048:
+        if (allow_4095 or e["N"] != 4095) and regs_cap >= (64 if f64 else 48) and e["T"] * e["minb"] * 2 <= 2048:
             out.append(dict(e, minb=e["minb"] * 2))
     return out
 
@@ -159,11 +159,13 @@ def real_entries(f64):
                 continue
             e = make(f64, N, TL, rad, rows_L(N, TL, rad[0], cs), 0, fam, always_smem=True)
             out.append(e)
+            if N in MIXED:
+                out.extend(capped_variants([e], f64, allow_4095=True))
             if fam == 1 and N >= 256 and N != 4095 and os.environ.get("NDFB_GEN_EXPERIMENT"):
                 mb = e["minb"] + 1
                 if e["smem"] * mb <= 227 * 1024 and e["T"] * mb <= 2048:
                     out.append(dict(e, minb=mb))
-        for N in [32, 64, 128, 256, 512, 1024, 2048, 4096, 132, 264]:
+        for N in [32, 64, 128, 256, 512, 1024, 2048, 4096, 132, 264, 4095]:
             sc = schedule(N, f64, fam)
             if sc is None:
                 continue
@@ -174,6 +176,11 @@ def real_entries(f64):
                     continue
                 e = make(f64, N, TL, rad, L, 1, fam, always_smem=True)
                 tmax = 1024 if (fam == 1 and e["E"] * (4 if f64 else 2) <= 32) else 512
+                if N == 4095:
+                    # DCT-I of 4096 points along a strided axis (BASELINE c4): a two-column tile of 1024 threads capped at
+                    # 64 registers beats the general kernel this length used before (8 % of the roofline)
+                    tmax = 1024
+                    e = dict(e, minb=1)
                 if e["T"] > tmax or e["T"] < 32 or e["smem"] > 200 * 1024:
                     continue
                 out.append(e)
