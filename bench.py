@@ -150,10 +150,10 @@ def run_reference(args):
 
 
 # per-launch DRAM traffic of the two bench kernels from `ncu --set full` captures of this same command (profiles/)
-ROWS_TRAFFIC = 1.027e9
-ROWS_TRAFFIC_SRC = "ncu --set full, profiles/r1v_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 489 MB per launch"
-COLS_TRAFFIC = 1.125e9
-COLS_TRAFFIC_SRC = "ncu --set full, profiles/r1v_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 588 MB per launch (both passes; the intermediate stays in L2)"
+ROWS_TRAFFIC = 1.028e9
+ROWS_TRAFFIC_SRC = "ncu --set full, profiles/r1z_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 491 MB per launch"
+COLS_TRAFFIC = 1.130e9
+COLS_TRAFFIC_SRC = "ncu --set full, profiles/r1z_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 593 MB per launch (both passes; the intermediate stays in L2)"
 
 
 def main():

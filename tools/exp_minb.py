@@ -29,10 +29,12 @@ def rnd(shape, rt, cx):
 
 # name, fn, in shape, out shape, axis, dtype, n, handler, env var, core N, (index of the current default, index of the variant)
 CASES = [
-    ("c4 dct1 rows f64", "nddct1", (4096, 4096), None, 1, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 4095, (0, 1)),
-    ("dct1 4096 rows f32", "nddct1", (8192, 4096), None, 1, np.float32, 4096, "DctHandler", "NDFB_RSFFT_PICK", 4095, (0, 1)),
-    ("c5a rows 384 f64", "ndfft", (360, 1000, 384), None, 2, np.float64, 384, "FftHandler", "NDFB_SFFT_PICK", 384, (0, 1)),
-    ("rows 360 f64", "ndfft", (200000, 360), None, 1, np.float64, 360, "FftHandler", "NDFB_SFFT_PICK", 360, (0, 1)),
+    ("c4 dct2 cols f64 idx2 vs idx3 (L=4 T=1024 vs L=2 T=512)", "nddct2", (4096, 4096), None, 0, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (2, 3)),
+    ("c4 dct2 cols f64 idx0 vs idx1 (family A)", "nddct2", (4096, 4096), None, 0, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (0, 1)),
+    ("c4 dct3 cols f64 idx2 vs idx3", "nddct3", (4096, 4096), None, 0, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (2, 3)),
+    ("c4 dct4 cols f64 idx2 vs idx3", "nddct4", (4096, 4096), None, 0, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 2048, (2, 3)),
+    ("c4 dct1 cols f64 (new tile; both default)", "nddct1", (4096, 4096), None, 0, np.float64, 4096, "DctHandler", "NDFB_RSFFT_PICK", 1, (0, 0)),
+    ("c2-like cols 4096 f64 idx default vs L=2", "ndfft", (4096, 8192), None, 0, np.float64, 4096, "FftHandler", "NDFB_SFFT_PICK", 1, (0, 0)),
 ]
 os.environ["NDFB_TRACE"] = "1"
 for name, fn, si, so, axis, dt, n, hk, var, core, idxs in CASES:
