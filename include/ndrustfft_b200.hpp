@@ -158,6 +158,41 @@ template <typename T> void nddct2(const ndview<T>& i, ndview<T>& o, const DctHan
 template <typename T> void nddct3(const ndview<T>& i, ndview<T>& o, const DctHandler<T>& h, size_t a) { nddct(NDFB_OP_DCT3, i, o, h, a); }
 template <typename T> void nddct4(const ndview<T>& i, ndview<T>& o, const DctHandler<T>& h, size_t a) { nddct(NDFB_OP_DCT4, i, o, h, a); }
 
+// ---- multi-axis compositions in one call (ndfb_exec_chain): the fft2 / rfft2 patterns of examples/fft2.rs:23-27, 55-59
+// and examples/rfft2.rs:29-33, 48-53, with the `work` array kept on the GPU.  Custom normalisation is a host callback:
+// compose the single calls for handlers that carry one. ----
+namespace detail {
+template <typename A, typename B>
+inline void chain(std::initializer_list<ndfb_step> steps, const ndview<A>& in, ndview<B>& out, void* stream = nullptr) {
+    if (in.ndim() != out.ndim()) throw std::runtime_error("input and output must have the same number of dimensions");
+    if (in.device != out.device) throw std::runtime_error("input and output must both be host or both be device arrays");
+    int rc = ndfb_exec_chain(steps.begin(), (int)steps.size(), in.data, out.data, (int)in.ndim(), in.shape.data(), in.strides.data(),
+                             out.shape.data(), out.strides.data(), in.device ? NDFB_MEM_DEVICE : NDFB_MEM_HOST, stream);
+    if (rc != 0) throw std::runtime_error(ndfb_last_error());
+}
+template <typename H> inline void no_custom(const H& h) {
+    if (h.norm_.kind == decltype(h.norm_)::Custom) throw std::runtime_error("chained transforms take None/Default normalisation; compose the single calls for Custom");
+}
+}  // namespace detail
+template <typename T>
+void fft2(const ndview<std::complex<T>>& in, ndview<std::complex<T>>& out, const FftHandler<T>& ax0, const FftHandler<T>& ax1) {
+    detail::chain({{ax1.plan_.get(), NDFB_OP_FFT, NDFB_NORM_NONE, 1}, {ax0.plan_.get(), NDFB_OP_FFT, NDFB_NORM_NONE, 0}}, in, out);
+}
+template <typename T>
+void ifft2(const ndview<std::complex<T>>& in, ndview<std::complex<T>>& out, const FftHandler<T>& ax0, const FftHandler<T>& ax1) {
+    detail::no_custom(ax0); detail::no_custom(ax1);
+    detail::chain({{ax0.plan_.get(), NDFB_OP_IFFT, norm_code(ax0.norm_), 0}, {ax1.plan_.get(), NDFB_OP_IFFT, norm_code(ax1.norm_), 1}}, in, out);
+}
+template <typename T>
+void rfft2(const ndview<T>& in, ndview<std::complex<T>>& out, const FftHandler<T>& ax0, const R2cFftHandler<T>& ax1) {
+    detail::chain({{ax1.plan_.get(), NDFB_OP_R2C, NDFB_NORM_NONE, 1}, {ax0.plan_.get(), NDFB_OP_FFT, NDFB_NORM_NONE, 0}}, in, out);
+}
+template <typename T>
+void irfft2(const ndview<std::complex<T>>& in, ndview<T>& out, const FftHandler<T>& ax0, const R2cFftHandler<T>& ax1) {
+    detail::no_custom(ax0); detail::no_custom(ax1);
+    detail::chain({{ax0.plan_.get(), NDFB_OP_IFFT, norm_code(ax0.norm_), 0}, {ax1.plan_.get(), NDFB_OP_C2R, norm_code(ax1.norm_), 1}}, in, out);
+}
+
 // `_par` twins (src/lib.rs:399-421, 589-611, 777-844): on the GPU every call already runs all lanes in parallel.
 template <typename... A> void ndfft_par(A&&... a) { ndfft(std::forward<A>(a)...); }
 template <typename... A> void ndifft_par(A&&... a) { ndifft(std::forward<A>(a)...); }

@@ -77,6 +77,33 @@ int main(int argc, char** argv) {
         ndifft_r2c(sv, bv, hc, 1);
         check(close_to(xb, tm, 1e-3), "c2r custom norm roundtrip");
     }
+    if (gpu) {
+        // examples/fft2.rs and examples/rfft2.rs through the one-call compositions
+        const double xin[9] = {1, 2, 3, 4, 5, 6, 7, 8, 9};
+        std::vector<cd> v(9), vhat(9), back(9), work(9), want(9);
+        for (int i = 0; i < 9; ++i) v[i] = cd(xin[i], xin[i]);
+        FftHandler<double> h0(3), h1(3);
+        auto vv = ndview<cd>::c_order(v.data(), {3, 3}); auto vh = ndview<cd>::c_order(vhat.data(), {3, 3});
+        auto vb = ndview<cd>::c_order(back.data(), {3, 3}); auto vw = ndview<cd>::c_order(work.data(), {3, 3}); auto vt = ndview<cd>::c_order(want.data(), {3, 3});
+        fft2(vv, vh, h0, h1);
+        ndfft(vv, vw, h1, 1); ndfft(vw, vt, h0, 0);
+        bool same = true;
+        for (int i = 0; i < 9; ++i) same = same && std::abs(vhat[i] - want[i]) < 1e-12;
+        check(same && std::abs(vhat[0] - cd(45, 45)) < 1e-9, "fft2 == two ndfft calls (examples/fft2.rs)");
+        ifft2(vh, vb, h0, h1);
+        for (int i = 0; i < 9; ++i) same = same && std::abs(back[i] - v[i]) < 1e-9;
+        check(same, "ifft2 roundtrip");
+        std::vector<double> x(xin, xin + 9), xb(9);
+        std::vector<cd> sp(6);
+        R2cFftHandler<double> hr(3);
+        auto xv = ndview<double>::c_order(x.data(), {3, 3}); auto sv = ndview<cd>::c_order(sp.data(), {3, 2}); auto bv = ndview<double>::c_order(xb.data(), {3, 3});
+        rfft2(xv, sv, h0, hr);
+        check(std::abs(sp[0] - cd(45, 0)) < 1e-9 && std::abs(sp[1] - cd(-4.5, 2.59808)) < 1e-4 && std::abs(sp[2] - cd(-13.5, 7.79423)) < 1e-4, "rfft2 (examples/rfft2.rs)");
+        irfft2(sv, bv, h0, hr);
+        bool rt = true;
+        for (int i = 0; i < 9; ++i) rt = rt && std::fabs(xb[i] - xin[i]) < 1e-9;
+        check(rt, "irfft2 roundtrip");
+    }
     std::printf(fails ? "MIRROR_FAIL %d\n" : "MIRROR_OK\n", fails);
     return fails ? 1 : 0;
 }

@@ -45,3 +45,17 @@ def test_cpp_mirror_reference_unit_tests(tmp_path):
     txt = _build(tmp_path)
     p = subprocess.run([EXE, txt, "gpu"], capture_output=True, text=True)
     assert p.returncode == 0 and "MIRROR_OK" in p.stdout, p.stdout + p.stderr
+
+
+def test_cpp_mirror_full_suite_against_the_emulation_build(tmp_path):
+    """The same C ABI is exported by the CPU emulation build of the kernels (tests/emu): run the whole C++ suite,
+    including the one-call fft2 / rfft2 compositions, without a GPU."""
+    emu_dir = os.path.join(ROOT, "tests", "emu")
+    if not os.path.exists(os.path.join(emu_dir, "libndfft_b200_emu.so")):
+        subprocess.check_call(["make", "-C", ROOT, "emu"], stdout=subprocess.DEVNULL)
+    txt = _build(tmp_path)
+    exe = os.path.join(ROOT, "build", "mirror_test_emu")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "mirror_test.cpp"),
+                           "-L", emu_dir, "-lndfft_b200_emu", f"-Wl,-rpath,{emu_dir}", "-o", exe])
+    p = subprocess.run([exe, txt, "gpu"], capture_output=True, text=True)
+    assert p.returncode == 0 and "MIRROR_OK" in p.stdout, p.stdout + p.stderr
