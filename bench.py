@@ -152,6 +152,8 @@ def run_reference(args):
 # per-launch DRAM traffic of the two bench kernels from `ncu --set full` captures of this same command (profiles/)
 ROWS_TRAFFIC = 1.028e9
 ROWS_TRAFFIC_SRC = "ncu --set full, profiles/r1z_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 491 MB per launch"
+COLS2_TRAFFIC = 2.05e9
+COLS2_TRAFFIC_SRC = "ncu, profiles/r1l_ncu_bench_summary.txt + r1t l2 probe: 537 MB read + 488-492 MB written per pass kernel, two pass kernels per call"
 COLS_TRAFFIC = 1.130e9
 COLS_TRAFFIC_SRC = "ncu --set full, profiles/r1z_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 593 MB per launch (both passes; the intermediate stays in L2)"
 
@@ -320,12 +322,16 @@ def main():
                 "ms": rows_ms, "achieved": BYTES_PER_TRANSFORM / (rows_ms * 1e-3) / 1e9,
                 "frac": BYTES_PER_TRANSFORM / (rows_ms * 1e-3) / 1e9 / peak, "share_of_step": (per[0] + per[3]) / sum(per),
                 "traffic": ROWS_TRAFFIC, "traffic_source": ROWS_TRAFFIC_SRC}
-        cols = {"kernel": ("fs2_kernel<float, Sched<64,...>, 64, Sched<128,...>, 32> (ndfft/ndifft along the strided axis: both column passes of "
-                           "8192 = 64 x 128 in one persistent launch, workspace ring in L2)") if strided_launches == 1 else
-                          "two sfft_kernel launches per call (64- and 128-point column passes through an HBM workspace)",
+        cols = {"kernel": ("fs2_kernel<float, Sched<64,...>, 64, Sched<128,...>, 32> (NDFB_FS2=1: both column passes of 8192 = 64 x 128 in one "
+                           "persistent launch, workspace ring in L2)") if strided_launches == 1 else
+                          "two sfft_kernel launches per call: 64-point then 128-point column passes through an HBM workspace (2 x 1 GiB moved)",
                 "launches_per_call": strided_launches, "ms": cols_ms, "achieved": BYTES_PER_TRANSFORM / (cols_ms * 1e-3) / 1e9,
                 "frac": BYTES_PER_TRANSFORM / (cols_ms * 1e-3) / 1e9 / peak, "share_of_step": (per[1] + per[2]) / sum(per),
-                "traffic": COLS_TRAFFIC if strided_launches == 1 else None, "traffic_source": COLS_TRAFFIC_SRC if strided_launches == 1 else None}
+                "traffic": COLS_TRAFFIC if strided_launches == 1 else COLS2_TRAFFIC,
+                "traffic_source": COLS_TRAFFIC_SRC if strided_launches == 1 else COLS2_TRAFFIC_SRC}
+        if strided_launches == 2:
+            # each pass kernel moves the whole array once in and once out: its own roofline fraction
+            cols["frac_of_bytes_moved_by_the_two_passes"] = 2 * BYTES_PER_TRANSFORM / (cols_ms * 1e-3) / 1e9 / peak
         # dominant kernel = the single kernel with the largest share of the step
         dom, other, other_key = (cols, rows, "contiguous_axis_kernel") if (strided_launches == 1 and cols["share_of_step"] >= rows["share_of_step"]) \
             else (rows, cols, "strided_axis_call")

@@ -637,12 +637,13 @@ template <typename R>
 static int exec_fs2(ndfb_plan* p, long long N, bool inverse, double scale, const void* in, void* out, const BDim& cols,
                     long long is_axis, long long os_axis, stream_t stream, int* done) {
     *done = 0;
-    if (std::getenv("NDFB_NO_FS2") || N > (1LL << 17)) return 0;
+    // Opt-in (NDFB_FS2=1).  Measured on B200 in the bench's c2 step (profiles/r1u_fused_two_pass.jsonl, r1z notes in
+    // DESIGN.md 4.4b): the fused launch halves the DRAM traffic (1.13 GB instead of 2.15 GB per call) but is bound by
+    // instruction issue / latency on the SMs (0.344 ms), while the two separate pass kernels, after the cursor addressing,
+    // each run at 98 % of the HBM copy peak (0.334 ms for both) -- so the two-launch path is the default again.
+    if (!std::getenv("NDFB_FS2") || std::getenv("NDFB_NO_FS2") || N > (1LL << 17)) return 0;
     const bool f64 = sizeof(R) == 8;
-    // measured on B200 (profiles/r1u_fused_two_pass.jsonl): c64 8192-point columns 0.407 -> 0.383 ms, c128 no gain
-    // (0.400 -> 0.404 ms), so double precision keeps the two-launch path unless asked
     if (f64 && !std::getenv("NDFB_FS2_F64")) return 0;
-    // longer columns (128 x 128, 256 x 256) measured slower fused than as two launches (0.40 vs 0.38 ms, 0.45 vs 0.42 ms)
     if (N != 8192 && !std::getenv("NDFB_FS2_ALL")) return 0;
     const size_t cs = sizeof(Cx<R>);
     const Fs2Entry* e = nullptr;

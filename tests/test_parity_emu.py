@@ -514,7 +514,7 @@ def test_fused_two_pass_columns(hs, capfd):
     """Long strided columns: both four-step passes in one persistent launch over an L2-sized workspace ring (fs2_kernel).
     NDFB_FS2_KB shrinks the group budget so that small arrays already form >= 4 groups."""
     import os
-    os.environ.update({"NDFB_TRACE": "1", "NDFB_FS2_KB": "4096", "NDFB_FS2_F64": "1", "NDFB_FS2_ALL": "1"})
+    os.environ.update({"NDFB_TRACE": "1", "NDFB_FS2": "1", "NDFB_FS2_KB": "4096", "NDFB_FS2_F64": "1", "NDFB_FS2_ALL": "1"})
     try:
         hs.run("ndfft", 8192, (8192, 256), 0, np.float32, seed=1)                    # 64 x 128, 4 groups of 64 columns
         hs.run("ndifft", 8192, (8192, 192), 0, np.float64, seed=2, norm="none")      # 6 groups of 32 columns: ring slots reused
@@ -528,7 +528,7 @@ def test_fused_two_pass_columns(hs, capfd):
         err = capfd.readouterr().err
         assert "[ndfb] fs2" not in err and err.count("[ndfb] four-step") == 2
     finally:
-        for k in ("NDFB_TRACE", "NDFB_FS2_KB", "NDFB_NO_FS2", "NDFB_FS2_F64", "NDFB_FS2_ALL"):
+        for k in ("NDFB_TRACE", "NDFB_FS2", "NDFB_FS2_KB", "NDFB_NO_FS2", "NDFB_FS2_F64", "NDFB_FS2_ALL"):
             os.environ.pop(k, None)
 
 

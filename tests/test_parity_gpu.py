@@ -494,32 +494,30 @@ def test_single_call_in_place_device(dev, op, n, shape, axis):
 
 
 def test_fused_two_pass_columns_device(dev):
-    # c2 axis 0 runs both column passes in one persistent launch (fs2_kernel); same bits as the two-launch path
+    # opt-in (NDFB_FS2=1): both column passes of c2 axis 0 in one persistent launch (fs2_kernel); same bits as the default
+    # two-launch path
     import os
     be = dev.be
     x = _rand((8192, 1024), np.float32, True, 21)
     h = be.FftHandler(8192, np.float32)
     y = torch.empty_like(x); y2 = torch.empty_like(x)
     l0 = be.lib.launch_count()
-    be.ndfft(x, y, h, 0)
-    assert be.lib.launch_count() - l0 == 1
-    os.environ["NDFB_NO_FS2"] = "1"
-    try:
-        l0 = be.lib.launch_count()
-        be.ndfft(x, y2, h, 0)
-        assert be.lib.launch_count() - l0 == 2
-    finally:
-        del os.environ["NDFB_NO_FS2"]
-    assert torch.equal(y, y2)
-    _lane_subset_check(be, "ndfft", 8192, x, y, 0, np.float32, nsample=16)
-    # inverse, in place, and a column count that is not a power of two (groups of 192 = 3 x 64 columns)
-    xi = _rand((8192, 960), np.float32, True, 22)
-    buf = xi.clone()
-    be.ndfft(buf, buf, h, 0); be.ndifft(buf, buf, h, 0)
-    assert _rel(buf, xi) < 1e-5
-    # double precision on request
+    be.ndfft(x, y2, h, 0)
+    assert be.lib.launch_count() - l0 == 2
+    os.environ["NDFB_FS2"] = "1"
     os.environ["NDFB_FS2_F64"] = "1"
     try:
+        l0 = be.lib.launch_count()
+        be.ndfft(x, y, h, 0)
+        assert be.lib.launch_count() - l0 == 1
+        assert torch.equal(y, y2)
+        _lane_subset_check(be, "ndfft", 8192, x, y, 0, np.float32, nsample=16)
+        # inverse, in place, and a column count that is not a power of two (groups of 192 = 3 x 64 columns)
+        xi = _rand((8192, 960), np.float32, True, 22)
+        buf = xi.clone()
+        be.ndfft(buf, buf, h, 0); be.ndifft(buf, buf, h, 0)
+        assert _rel(buf, xi) < 1e-5
+        # double precision on request
         xd = _rand((8192, 512), np.float64, True, 23)
         hd = be.FftHandler(8192, np.float64)
         yd = torch.empty_like(xd)
@@ -529,6 +527,7 @@ def test_fused_two_pass_columns_device(dev):
         _lane_subset_check(be, "ndfft", 8192, xd, yd, 0, np.float64, nsample=16)
     finally:
         del os.environ["NDFB_FS2_F64"]
+        del os.environ["NDFB_FS2"]
 
 
 def test_workspace_reuse_across_streams(dev):

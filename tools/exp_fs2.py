@@ -26,8 +26,8 @@ def rnd(shape, rt):
 
 
 CASES = [("c2 cols 8192 f32", (8192, 8192), np.float32, 8192),
-         ("cols 8192 f64", (8192, 4096), np.float64, 8192),
-         ("cols 65536 f32", (65536, 1024), np.float32, 65536)]
+         ("cols 16384 f32", (16384, 4096), np.float32, 16384)]
+os.environ["NDFB_FS2_ALL"] = "1"
 for name, shape, dt, n in CASES:
     rt = torch.float32 if dt == np.float32 else torch.float64
     x = rnd(shape, rt); y = torch.empty_like(x)
@@ -39,7 +39,7 @@ for name, shape, dt, n in CASES:
     print(json.dumps({"case": name, "variant": "two launches", "ms": round(ms, 4), "frac": round(nbytes / (ms * 1e-3) / 1e9 / PEAK, 3)}), flush=True)
     del os.environ["NDFB_NO_FS2"]
     os.environ["NDFB_FS2_F64"] = "1"
-    for kb, ring, dbg, T in ((8192, 3, 0, 256), (8192, 3, 0, 128), (4096, 3, 0, 128), (16384, 3, 0, 128), (8192, 4, 0, 128), (4096, 4, 0, 256), (8192, 3, 3, 128)):
+    for kb, ring, dbg, T in ((8192, 3, 0, 256), (8192, 3, 0, 512), (16384, 3, 0, 512), (16384, 4, 0, 512), (32768, 3, 0, 512), (8192, 3, 3, 512), (8192, 3, 3, 256)):
         os.environ["NDFB_FS2_KB"] = str(kb); os.environ["NDFB_FS2_RING"] = str(ring); os.environ["NDFB_FS2_DBG"] = str(dbg); os.environ["NDFB_FS2_T"] = str(T)
         y.zero_()
         ms = timeit(lambda: nb.ndfft(x, y, h, 0))

@@ -224,7 +224,7 @@ def fs2_entries():
             r1 = r1 + [1] * (4 - len(r1))
             r2 = r2 + [1] * (4 - len(r2))
             R = "double" if f64 else "float"
-            for T in (256, 128):          # first match is the default; NDFB_FS2_T picks the other
+            for T in (256, 128, 512):     # first match is the default; NDFB_FS2_T picks another
                 L1, L2 = T // TL1, T // TL2
                 if min(L1, L2) * (16 if f64 else 8) < 64:
                     continue
