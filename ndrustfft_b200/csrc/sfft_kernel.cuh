@@ -609,8 +609,42 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
         __syncthreads();
     }
 
+    // ---- C2R / DCT-III "zip" prologue, pairwise: slots j and N-j are built from the same two spectrum bins
+    // (E = X[j] + conj(X[N-j]), O = X[j] - conj(X[N-j]), w = conj(tabA[j]) O:  z[j] = conj(E + i w),  z[N-j] = E - i w,
+    // because tabA[N-j] = -conj(tabA[j])), so one thread loads them once and writes both slots to the shared buffer;
+    // the first pass then reads plain complex slots.  Halves the global/table loads and the prologue arithmetic. ----
+    constexpr bool PAIR_PRO = KIND == RK_C2R || KIND == RK_DCT3;
+    if (PAIR_PRO) {
+        constexpr int ITQ = (N / 2 + 1 + S::TL - 1) / S::TL;
+#pragma unroll
+        for (int m = 0; m < ITQ; ++m) {
+            const int j = c.i + m * S::TL;
+            if (j > N / 2) break;
+            const int k2 = N - j;
+            Cx<R> xk, xn;
+            if (KIND == RK_C2R) {
+                xk = valid ? in_c[(long long)j * is_axis] : cmake<R>(zero, zero);
+                xn = valid ? in_c[(long long)k2 * is_axis] : cmake<R>(zero, zero);
+                if (j == 0) { xk.y = zero; xn.y = zero; }        // Im X[0], Im X[N] dropped (src/lib.rs:516-521)
+            } else {
+                // P[k] = (y[k], -y[n-k]) with y[n] = 0, then V[k] = conj(t_k) P[k]
+                Cx<R> pk = cmake<R>(gin(j), j == 0 ? zero : -gin(n - j));
+                Cx<R> pn = cmake<R>(gin(k2), -gin(n - k2));
+                xk = cmul(pk, cconj(ldg(&tabB[j])));
+                xn = cmul(pn, cconj(ldg(&tabB[k2])));
+            }
+            const Cx<R> wc = cconj(ldg(&tabA[j]));
+            const Cx<R> E = cadd(xk, cconj(xn)), O = csub(xk, cconj(xn));
+            const Cx<R> iw = cmul_i(cmul(wc, O));
+            c.smem[c.addr(j)] = cconj(cadd(E, iw));
+            if (j != 0 && k2 != j) c.smem[c.addr(k2)] = csub(E, iw);
+        }
+        __syncthreads();
+    }
+
     // ---- first-pass input z[j], j < N ----
     auto load = [&](int j) -> Cx<R> {
+        if (PAIR_PRO) return c.smem[c.addr(j)];
         if (KIND == RK_R2C) {
             if (!COLS && is_axis == 1) {   // (x[2j], x[2j+1]) is one aligned complex load
                 return valid ? reinterpret_cast<const Cx<R>*>(in_r)[j] : cmake<R>(zero, zero);
@@ -679,7 +713,7 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     };
 
     Cx<R> v[S::E];
-    SfftAll<R, S, L, COLS, 0, STAGE_IN, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
+    SfftAll<R, S, L, COLS, 0, STAGE_IN || PAIR_PRO, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
 
     if (PAIR_EPI) {
         __syncthreads();
