@@ -226,6 +226,7 @@ struct LaunchSpec {
     void* blk_ptr[8] = {nullptr};
     ndfb_plan::FsTw fs;
     bool keep_dim_order = false;
+    int max_L = 0;    // != 0: widest tile allowed (transposing passes want 32/L points of a lane per warp >= one sector)
 };
 
 // ---- fast path lookup ----
@@ -277,7 +278,7 @@ static bool better_entry(const E* e, const E* best, long long nlanes, int pref_f
     return e->L > best->L;
 }
 
-static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes, long long axis_stride_bytes = 0) {
+static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes, long long axis_stride_bytes = 0, int max_L = 0) {
     static const bool disabled = std::getenv("NDFB_DISABLE_SFFT") != nullptr;
     if (disabled) return nullptr;
     const SfftEntry* tabs[4] = {kSfft_f32_rows, kSfft_f32_cols, kSfft_f64_rows, kSfft_f64_cols};
@@ -297,6 +298,7 @@ static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes, 
     for (int i = 0; i < counts[which]; ++i) {
         const SfftEntry* e = &tabs[which][i];
         if (e->N != N) continue;
+        if (max_L && e->L > max_L) continue;
         if (better_entry(e, best, nlanes, pref, f64 ? (size_t)16 : (size_t)8, axis_stride_bytes)) best = e;
     }
     return best;
@@ -467,7 +469,8 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         const bool have_batch = !s.dims.empty() && nlanes > 1;
         const bool cols = have_batch && t.N > 1 &&
                           (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
-        const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
+        const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>), s.max_L);
+        if (!e && s.max_L) e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
             if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
@@ -843,6 +846,20 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     s1.conj_in = conj_in; s1.fs_twiddle = 1; s1.fs = fs;
     if ((rc = launch_c2c<R>(p, s1, stream))) return rc;
     s2.conj_out = inverse; s2.scale = scale;
+    if (!nested2 && !strided && (depth > 0 || std::getenv("NDFB_FS_TRANSPOSE")) && !std::getenv("NDFB_NO_FS_TRANSPOSE")) {
+        // Transposing last pass of the three-pass split: tile the lanes along the dim that is contiguous in the OUTPUT (the
+        // outer level's k1, output stride 1) instead of the one contiguous in the workspace, and cap the tile at 8 lanes
+        // so that a warp still reads 32/L consecutive points (>= one 32-byte sector) of each lane's row.  Measured on
+        // B200, 64 x 2^24 c64 as 256 x (256 x 256): 21.96 -> 12.21 ms (profiles/r2b_c5b_three_pass.jsonl); the two-pass
+        // 4096 x 4096 split (11.2 ms) still wins where it fits, so this matters for lengths beyond two on-chip factors.
+        size_t best = 0;
+        for (size_t d = 1; d < s2.dims.size(); ++d)
+            if (llabs_(s2.dims[d].os) < llabs_(s2.dims[best].os)) best = d;
+        if (best != 0) {
+            std::swap(s2.dims[0], s2.dims[best]);
+            s2.max_L = sizeof(R) == 8 ? 16 : 8;
+        }
+    }
     {
         const bool trace = std::getenv("NDFB_TRACE") != nullptr;
         if (trace) fprintf(stderr, "[ndfb] four-step N=%lld = %lld x %lld (%s lanes%s)\n", N, N1, N2, strided ? "strided" : "contiguous", nested2 ? ", second factor split again" : "");
