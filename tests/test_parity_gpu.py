@@ -547,3 +547,23 @@ def test_workspace_reuse_across_streams(dev):
             be.ndfft(x2, y2, h, 1)
     torch.cuda.synchronize()
     assert torch.equal(y1, w1) and torch.equal(y2, w2)
+
+
+def test_three_pass_split_matches_two_pass(dev):
+    # 2^24-point rows as 256 x (256 x 256) (forced; the default is 4096 x 4096): the nested level's last pass tiles the lanes
+    # along the output-contiguous dim (transposing pass).  Same transform, different factorisation: equal within f32 rounding.
+    import os
+    be = dev.be
+    n = 1 << 24
+    x = _rand((2, n), np.float32, True, 41)
+    h = be.FftHandler(n, np.float32)
+    y2 = torch.empty_like(x); y3 = torch.empty_like(x)
+    be.ndfft(x, y2, h, 1)
+    os.environ["NDFB_FS_N1"] = "256"
+    try:
+        be.ndfft(x, y3, h, 1)
+        assert _rel(y3, y2) < 2e-6
+        be.ndifft(y3, y3, h, 1)          # in place through the three-pass path
+        assert _rel(y3, x) < 2e-6
+    finally:
+        del os.environ["NDFB_FS_N1"]
