@@ -9,6 +9,11 @@ Two schedule families are instantiated and the host picks per case (csrc/ndfft_b
   family B: more CTAs per SM            (radix 8 for f64, 16 for f32;      E = 8/16 points per thread)
 Measured on B200 (profiles/r1f_tune*.jsonl): B wins wherever occupancy is the limiter (e.g. 512-point f64 rows
 81 % vs 64 % of the HBM roofline).
+
+Also generated: the fused Bluestein kernels (bsfft_inst_*.cu), the fused two-pass column kernels (fs2_inst.cu, opt-in at
+run time) and, for the mixed-radix lengths, register-capped variants of the same tiles (capped_variants: twice the CTAs
+per SM for 8-16 bytes of spill, 1.2-1.5x faster; the host picks them through its resident-thread rule).
+`NDFB_GEN_EXPERIMENT=1` adds extra-CTA variants of the power-of-two kernels for A/B runs (they lose; not committed).
 """
 import os
 import sys
