@@ -45,7 +45,7 @@ def relayout(a, how, rng):
 LAYOUTS = ["C", "F", "strided", "reversed", "transposed"]
 
 
-@settings(max_examples=400, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=400, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
 @given(op=st.sampled_from(OPS), n=st.sampled_from(LENGTHS), batch=st.lists(st.integers(1, 5), min_size=0, max_size=3),
        axis_pos=st.integers(0, 3), lin=st.sampled_from(LAYOUTS), lout=st.sampled_from(LAYOUTS),
        norm=st.sampled_from(["default", "none"]), f32=st.booleans(), seed=st.integers(0, 2 ** 16))
@@ -74,3 +74,66 @@ def test_any_layout_any_length(hs, op, n, batch, axis_pos, lin, lout, norm, f32,
     # tolerance: the north-star relative L2 bound; longer prime lengths in f32 go through Bluestein (two transforms)
     err = orc.rel_l2(np.asarray(y), want)
     assert err <= TOL[rd], f"{op} n={n} shape={shape} axis={axis} {rd} {lin}->{lout} norm={norm}: rel L2 {err:.3e}"
+
+
+# ---- multi-axis chains: random sequences of steps over random axes and layouts against the step-by-step oracle ----
+@settings(max_examples=150, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
+@given(data=st.data())
+def test_any_chain(hs, data):
+    ndim = data.draw(st.integers(1, 3))
+    shape = [data.draw(st.sampled_from([2, 3, 4, 5, 6, 8, 9, 12, 16])) for _ in range(ndim)]
+    rd = np.dtype(data.draw(st.sampled_from([np.float32, np.float64])))
+    nsteps = data.draw(st.integers(1, 4))
+    cplx = data.draw(st.booleans())          # element type of the array the chain starts from
+    cur_shape = list(shape)
+    steps = []
+    start_cplx = cplx
+    for _ in range(nsteps):
+        axis = data.draw(st.integers(0, ndim - 1))
+        n_here = cur_shape[axis]
+        if cplx:
+            ops = ["ndfft", "ndifft"]
+            # c2r along this axis: n_here = m = n/2 + 1  ->  n in {2m-2, 2m-1}
+            if n_here >= 2:
+                ops.append("ndifft_r2c")
+        else:
+            ops = ["ndfft_r2c", "nddct2", "nddct3", "nddct4"] + (["nddct1"] if n_here >= 2 else [])
+        op = data.draw(st.sampled_from(ops))
+        if op == "ndifft_r2c":
+            n = data.draw(st.sampled_from([2 * n_here - 2, 2 * n_here - 1]))
+            if n < 1:
+                n = 1
+            cur_shape[axis] = n
+            cplx = False
+        elif op == "ndfft_r2c":
+            n = n_here
+            cur_shape[axis] = n // 2 + 1
+            cplx = True
+        else:
+            n = n_here
+        steps.append((op, n, axis))
+    lin = data.draw(st.sampled_from(LAYOUTS)); lout = data.draw(st.sampled_from(LAYOUTS))
+    norm = data.draw(st.sampled_from(["default", "none"]))
+    seed = data.draw(st.integers(0, 2 ** 16))
+    rng = np.random.default_rng(seed)
+    x = relayout(seeded(seed, tuple(shape), rd, start_cplx), lin, rng)
+    hs_steps, cur = [], np.asarray(x).astype(np.complex128 if start_cplx else np.float64)
+    for op, n, axis in steps:
+        hk, _, ocx = Harness.OPS[op]
+        h = getattr(hs.be, hk)(n, rd)
+        ho = getattr(orc, hk)(n)
+        if norm == "none":
+            h.normalization(type(h.norm).None_)
+            ho.normalization(orc.Normalization.none())
+        hs_steps.append((op, h, axis))
+        _, sout = hs.shapes(op, n, cur.shape, axis)
+        nxt = np.zeros(sout, np.complex128 if ocx else np.float64)
+        getattr(orc, op)(cur, nxt, ho, axis)
+        cur = nxt
+    y = relayout(np.zeros(cur.shape, cdt(rd) if cplx else rd), lout, rng)
+    x0 = x.copy()
+    hs.be.ndchain(x, y, hs_steps)
+    assert np.array_equal(x, x0), "input was modified"
+    scale = max(1.0, float(np.linalg.norm(cur)))
+    err = float(np.linalg.norm(np.asarray(y) - cur)) / scale
+    assert err <= 4 * TOL[rd], f"chain {steps} shape={shape} {rd} {lin}->{lout} norm={norm}: rel L2 {err:.3e}"
