@@ -473,7 +473,7 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         if (!e && s.max_L) e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
-            if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
+            if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A');
             return launch_sfft<R>(p, e, s, stream);
         }
     }
@@ -587,7 +587,7 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         const RsfftEntry* e = ok ? find_rsfft(sizeof(R) == 8, rk, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(R)) : nullptr;
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
-            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes);
+            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A');
             RsfftArgs a;
             std::memset(&a, 0, sizeof a);
             a.in = s.in; a.out = s.out; a.nlanes = nlanes;

@@ -542,3 +542,42 @@ def test_dct1_4096_strided_axis_runs_the_4095_point_tile(hs, capfd):
         del os.environ["NDFB_TRACE"]
     err = capfd.readouterr().err
     assert err.count("[ndfb] rsfft kind=2") == 2 and "N=4095 cols L=2" in err, err
+
+
+def test_schedule_selection_for_the_baseline_shapes(hs, capfd):
+    """The host's tile / variant choice for the BASELINE shapes (selection rules in find_sfft / find_rsfft; measured A/B
+    behind each rule in profiles/): regression guard, run on scaled-down batches (the rules look at strides, not at counts)."""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    be = hs.be
+    try:
+        def trace(fn, h, shape_in, shape_out, axis, cplx_in=True, cplx_out=True, rd=np.float64):
+            cd_ = np.complex128 if rd == np.float64 else np.complex64
+            x = np.zeros(shape_in, cd_ if cplx_in else rd); y = np.zeros(shape_out, cd_ if cplx_out else rd)
+            capfd.readouterr()
+            getattr(be, fn)(x, y, h, axis)
+            return capfd.readouterr().err
+        # c5a: mixed-radix c128, register-capped variants (2 CTAs/SM) on every axis
+        e = trace("ndfft", be.FftHandler(360), (360, 8, 384), (360, 8, 384), 0)
+        assert "N=360 cols L=8 T=480" in e and "minb=2" in e, e
+        e = trace("ndfft", be.FftHandler(1000), (2, 1000, 384), (2, 1000, 384), 1)
+        assert "N=1000 cols L=4 T=400" in e and "minb=2" in e, e
+        e = trace("ndfft", be.FftHandler(384), (2, 8, 384), (2, 8, 384), 2)
+        assert "N=384 rows L=4 T=256" in e and "minb=4" in e, e
+        # c3: 512-point c128 columns take the 8-lane family-B tile; r2c rows the 256-point core
+        e = trace("ndfft", be.FftHandler(512), (512, 16, 257), (512, 16, 257), 0)
+        assert "N=512 cols L=8 T=512" in e and "fam=B" in e, e
+        e = trace("ndfft_r2c", be.R2cFftHandler(512), (4, 4, 512), (4, 4, 257), 2, cplx_in=False)
+        assert "rsfft kind=0 f64 N=256 rows L=8 T=256" in e, e
+        # c4: DCT-I of 4096 points = 4095-point core, capped row variant and the two-column strided tile
+        e = trace("nddct1", be.DctHandler(4096), (2, 4096), (2, 4096), 1, cplx_in=False, cplx_out=False)
+        assert "N=4095 rows L=1 T=512" in e and "minb=2" in e, e
+        e = trace("nddct1", be.DctHandler(4096), (4096, 4), (4096, 4), 0, cplx_in=False, cplx_out=False)
+        assert "N=4095 cols L=2 T=1024" in e, e
+        # c2: 8192-point c64 rows = family B 16.16.16.2 with 512 threads; strided columns = two passes 64 x 128
+        e = trace("ndfft", be.FftHandler(8192, np.float32), (2, 8192), (2, 8192), 1, rd=np.float32)
+        assert "N=8192 rows L=1 T=512" in e and "fam=B" in e and "minb=2" in e, e
+        e = trace("ndfft", be.FftHandler(8192, np.float32), (8192, 64), (8192, 64), 0, rd=np.float32)
+        assert "four-step N=8192 = 64 x 128 (strided lanes)" in e and "fs2" not in e, e
+    finally:
+        del os.environ["NDFB_TRACE"]
