@@ -4,6 +4,8 @@ CXX       ?= g++
 CSRC      := ndrustfft_b200/csrc
 SRCS      := $(CSRC)/ndfft_b200.cu $(sort $(wildcard $(CSRC)/sfft_inst_*.cu) $(wildcard $(CSRC)/rsfft_inst_*.cu) $(wildcard $(CSRC)/bsfft_inst_*.cu) $(wildcard $(CSRC)/fs2_inst*.cu))
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh $(CSRC)/*.inc) include/ndfft_b200.h
+# the generated instantiation files only see the kernel headers: host-side edits do not rebuild ~900 kernel instances
+KHDRS     := $(CSRC)/common.h $(CSRC)/devapi.h $(CSRC)/butterflies.cuh $(CSRC)/sfft_kernel.cuh $(CSRC)/sfft_inst.h $(CSRC)/rsfft_tables.inc include/ndfft_b200.h
 LIBDIR    := ndrustfft_b200/lib
 LIB       := $(LIBDIR)/libndfft_b200.so
 EMULIB    := tests/emu/libndfft_b200_emu.so
@@ -19,11 +21,19 @@ all: $(LIB) $(EMULIB)
 lib: $(LIB)
 emu: $(EMULIB)
 
-$(OBJDIR)/cuda/%.o: $(CSRC)/%.cu $(HDRS)
+$(OBJDIR)/cuda/ndfft_b200.o: $(CSRC)/ndfft_b200.cu $(HDRS)
 	@mkdir -p $(OBJDIR)/cuda
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(OBJDIR)/emu/%.o: $(CSRC)/%.cu $(HDRS) tests/emu/simt_emu.h
+$(OBJDIR)/cuda/%.o: $(CSRC)/%.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)/cuda
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(OBJDIR)/emu/ndfft_b200.o: $(CSRC)/ndfft_b200.cu $(HDRS) tests/emu/simt_emu.h
+	@mkdir -p $(OBJDIR)/emu
+	$(CXX) $(CXXFLAGS) -x c++ -c -o $@ $<
+
+$(OBJDIR)/emu/%.o: $(CSRC)/%.cu $(KHDRS) tests/emu/simt_emu.h
 	@mkdir -p $(OBJDIR)/emu
 	$(CXX) $(CXXFLAGS) -x c++ -c -o $@ $<
 

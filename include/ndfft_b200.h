@@ -82,8 +82,14 @@ NDFB_API size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap)
 
 /* One nd* call.  shape/strides describe `in` and `out` as ndarray does: `ndim` extents and SIGNED strides
  * in ELEMENTS of the respective element type (real scalar, or interleaved {re,im} complex).  `mem` says
- * whether both pointers are host memory (copied through pinned staging; synchronous) or device memory on
- * the plan's device (asynchronous on `stream`, a cudaStream_t; NULL = default stream).
+ * whether both pointers are host memory (synchronous) or device memory on the plan's device (asynchronous on
+ * `stream`, a cudaStream_t; NULL = default stream).
+ * Host memory may be PAGEABLE (what ndarray's as_ptr() hands the Rust shim, src/lib.rs:105-115): large C-ordered
+ * arrays are cut into pieces and pipelined  caller memory -> pinned ring slot (copy threads) -> H2D | kernel | D2H ->
+ * pinned ring slot -> caller memory;  pointers that are already pinned or cudaHostRegister'ed skip the ring.
+ * Views with gaps between their elements are packed / unpacked on the host: the library never reads or writes a byte of
+ * host memory that is not a logical element of the view (sibling views of one allocation stay intact).
+ * Environment: NDFB_HOST_THREADS (copy threads, default min(8, cores/2)), NDFB_STAGE_MB (slot size, default 16).
  * In place: `in == out` with identical shape and strides is supported for the ops that keep shape and element type
  * (FFT, IFFT, DCT1..4) — every tile is read completely before it is written (the reference always takes a separate
  * output, src/lib.rs:107).  Partially overlapping arrays are not supported. */

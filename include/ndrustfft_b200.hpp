@@ -66,6 +66,8 @@ inline void exec(const ndfb_plan* plan, int op, int norm, const ndview<A>& in, n
 // call f on every lane of a HOST view along `axis`
 template <typename E, typename F>
 inline void for_each_lane(ndview<E>& v, size_t axis, F f) {
+    // Normalization::Custom is a HOST callback (src/lib.rs:95-97): it cannot walk device memory
+    if (v.device) throw std::runtime_error("Normalization::Custom needs host arrays (the callback runs on the host); use None/Default or host views");
     const size_t n = v.shape[axis];
     size_t lanes = 1;
     for (size_t d = 0; d < v.ndim(); ++d) if (d != axis) lanes *= v.shape[d];
@@ -80,6 +82,7 @@ inline void for_each_lane(ndview<E>& v, size_t axis, F f) {
 }
 template <typename E>
 inline std::vector<E> copy_dense(const ndview<E>& v, ndview<E>& dense) {
+    if (v.device) throw std::runtime_error("Normalization::Custom needs host arrays (the callback runs on the host); use None/Default or host views");
     size_t total = 1;
     for (size_t s : v.shape) total *= s;
     std::vector<E> buf(total);

@@ -127,11 +127,28 @@ class _View:
     __slots__ = ("ptr", "shape", "strides", "dtype", "device", "obj", "stream")
 
 
-def _view_of(arr):
+def _span(v):
+    """[lo, hi) byte range touched by a view."""
+    item = v.dtype.itemsize
+    lo = hi = 0
+    for n, s in zip(v.shape, v.strides):
+        if n == 0:
+            return v.ptr, v.ptr
+        ext = (n - 1) * s * item
+        if ext < 0:
+            lo += ext
+        else:
+            hi += ext
+    return v.ptr + lo, v.ptr + hi + item
+
+
+def _view_of(arr, out=False):
     v = _View()
     v.obj = arr
     v.stream = None
     if isinstance(arr, np.ndarray):
+        if out and not arr.flags.writeable:
+            raise ValueError("output array is read-only")
         item = arr.dtype.itemsize
         for s in arr.strides:
             if s % item:
@@ -144,6 +161,9 @@ def _view_of(arr):
         return v
     if hasattr(arr, "data_ptr") and hasattr(arr, "stride"):  # torch tensor
         import torch
+        # lazy conjugate / negative views share the storage of the original: the kernels would read the unflagged values
+        if (arr.is_complex() and arr.is_conj()) or arr.is_neg():
+            raise ValueError("tensor is a lazy conj/neg view; call .resolve_conj() / .resolve_neg() first")
         v.ptr = arr.data_ptr()
         v.shape = tuple(arr.shape)
         v.strides = tuple(arr.stride())
@@ -165,7 +185,12 @@ class Backend:
         self.lib = lib
 
     def _exec(self, handler, op, inp, out, axis, norm_code, extra_scale=1.0):
-        vi, vo = _view_of(inp), _view_of(out)
+        vi, vo = _view_of(inp), _view_of(out, out=True)
+        if op in (_lib.OP_R2C, _lib.OP_C2R):
+            # in place is part of the contract only for the ops that keep shape and element type
+            (a0, a1), (b0, b1) = _span(vi), _span(vo)
+            if a0 < b1 and b0 < a1:
+                raise ValueError("input and output overlap: ndfft_r2c / ndifft_r2c cannot run in place")
         if len(vi.shape) != len(vo.shape):
             raise AssertionError("input and output must have the same number of dimensions")
         ndim = len(vi.shape)
@@ -197,7 +222,7 @@ class Backend:
         """ndfft / ndifft on device tensors with the output axis stored in blocks (ndfb_exec_split_out): element k of an
         output lane lands at `(k // out_block) * out_block_stride + (k % out_block) * out_strides[axis]` from the lane base.
         `output` only provides the base pointer; `out_shape` / `out_strides` describe the logical output array."""
-        vi, vo = _view_of(input), _view_of(output)
+        vi, vo = _view_of(input), _view_of(output, out=True)
         if (vi.device is None or vo.device is None) and "emu" not in self.lib.version():
             raise ValueError("split-output transforms take device tensors")
         ndim = len(vi.shape)
@@ -297,7 +322,7 @@ class Backend:
                 raise ValueError(f"unknown transform {name!r}")
         if any(h.norm.kind == "custom" for _, h, _ in steps):
             return self._chain_stepwise(input, output, steps)
-        vi, vo = _view_of(input), _view_of(output)
+        vi, vo = _view_of(input), _view_of(output, out=True)
         if len(vi.shape) != len(vo.shape):
             raise AssertionError("input and output must have the same number of dimensions")
         ndim = len(vi.shape)

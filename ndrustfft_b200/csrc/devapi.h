@@ -54,7 +54,7 @@ inline int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stre
     launch_counter()++;
     return 0;
 }
-inline const char* version_string() { return "ndfft_b200 0.1 emu (CPU SIMT emulation, tests only)"; }
+inline const char* version_string() { return "ndfft_b200 0.2 emu (CPU SIMT emulation, tests only)"; }
 #else
 typedef cudaStream_t stream_t;
 inline int cuda_fail(cudaError_t e, const char* what) {
@@ -113,7 +113,7 @@ inline int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stre
     launch_counter()++;
     return 0;
 }
-inline const char* version_string() { return "ndfft_b200 0.1 sm_100a"; }
+inline const char* version_string() { return "ndfft_b200 0.2 sm_100a"; }
 #endif
 
 

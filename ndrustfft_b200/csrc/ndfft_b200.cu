@@ -19,6 +19,7 @@
 #include "../../include/ndfft_b200.h"
 #include "common.h"
 #include "devapi.h"
+#include "hostio.h"
 #include "plan.h"
 #include "big_kernels.cuh"
 #include "sfft_inst.h"
@@ -1095,6 +1096,28 @@ static int exec_big(ndfb_plan* p, const OpInfo& o, double scale, const void* in,
     return 0;
 }
 
+// Runs body(in', out', dims', blk') once per index combination of the batch dims beyond the `lim` fastest ones
+// (dims are normalised: fastest input stride first), with the pointers advanced accordingly.  The reference accepts any
+// ndarray Dimension (src/lib.rs:105-115), so views with many non-mergeable dims must work on every path.
+template <typename F>
+static int peel_batch_dims(const std::vector<BDim>& dims, int lim, size_t ie, size_t oe, const void* in, void* out,
+                           void* const* blk_ptr, int nblk, F&& body) {
+    if ((int)dims.size() <= lim) return body(in, out, dims, blk_ptr);
+    std::vector<BDim> inner(dims.begin(), dims.begin() + lim);
+    std::vector<BDim> outer(dims.begin() + lim, dims.end());
+    long long nouter = 1;
+    for (auto& d : outer) nouter *= d.size;
+    for (long long g = 0; g < nouter; ++g) {
+        long long rem = g, io = 0, oo = 0;
+        for (auto& d : outer) { long long r = rem % d.size; rem /= d.size; io += r * d.is; oo += r * d.os; }
+        void* blk[8] = {nullptr};
+        for (int i = 0; i < nblk && i < 8; ++i) blk[i] = (char*)blk_ptr[i] + oo * (long long)oe;
+        int rc = body((const char*)in + io * (long long)ie, (char*)out + oo * (long long)oe, inner, nblk ? blk : blk_ptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 template <typename R>
 static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, int ndim,
                        const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
@@ -1150,39 +1173,28 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
     }
     if (!single && o.os_blk) return fail(NDFB_E_UNSUPPORTED, "split output axis is only available for single-pass complex transforms");
     if (single && !o.os_blk && std::getenv("NDFB_FORCE_STAGED") && p->n >= 3) single = false;
+    const size_t ie = (o.in_complex ? 2 : 1) * sizeof(R), oe = (o.out_complex ? 2 : 1) * sizeof(R);
+    normalize_dims(dims);
     if (!single) {
-        if (o.tk == TK_C2C && is_smooth((long long)p->n) && !std::getenv("NDFB_FORCE_STAGED"))
-            return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, in, out, dims, is_axis, os_axis, stream);
-        return exec_big<R>(p, o, scale, in, out, dims, is_axis, os_axis, stream);
+        // the multi-pass paths index fewer batch dims in their kernels (the passes add dims of their own): peel the rest
+        const bool four_step = o.tk == TK_C2C && is_smooth((long long)p->n) && !std::getenv("NDFB_FORCE_STAGED");
+        int lim = kMaxBatchDims;
+        if (four_step) lim = ((long long)p->n > (1LL << 24) || std::getenv("NDFB_FS_CAP")) ? kMaxBatchDims - 2 : kMaxBatchDims - 1;
+        return peel_batch_dims(dims, lim, ie, oe, in, out, nullptr, 0, [&](const void* pin, void* pout, const std::vector<BDim>& d2, void* const*) -> int {
+            if (four_step) return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, pin, pout, d2, is_axis, os_axis, stream);
+            return exec_big<R>(p, o, scale, pin, pout, d2, is_axis, os_axis, stream);
+        });
     }
     if ((rc = ensure_device<R>(p, c))) return rc;
-    normalize_dims(dims);
-    // more batch dims than the kernel indexes: peel the slowest ones on the host
-    if ((int)dims.size() > kMaxBatchDims) {
-        std::vector<BDim> inner(dims.begin(), dims.begin() + kMaxBatchDims);
-        std::vector<BDim> outer(dims.begin() + kMaxBatchDims, dims.end());
-        long long nouter = 1;
-        for (auto& d : outer) nouter *= d.size;
-        const size_t ie = (o.in_complex ? 2 : 1) * sizeof(R), oe = (o.out_complex ? 2 : 1) * sizeof(R);
-        for (long long g = 0; g < nouter; ++g) {
-            long long rem = g, io = 0, oo = 0;
-            for (auto& d : outer) { long long r = rem % d.size; rem /= d.size; io += r * d.is; oo += r * d.os; }
-            LaunchSpec s;
-            s.core = c; s.in = (const char*)in + io * (long long)ie; s.out = (char*)out + oo * (long long)oe;
-            s.dims = inner; s.is_axis = is_axis; s.os_axis = os_axis;
-            s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-            s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride; s.nblk_ptr = o.nblk_ptr;
-            for (int i = 0; i < 8; ++i) s.blk_ptr[i] = o.blk_ptr[i];
-            if ((rc = (o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream)))) return rc;
-        }
-        return 0;
-    }
-    LaunchSpec s;
-    s.core = c; s.in = in; s.out = out; s.dims = dims; s.is_axis = is_axis; s.os_axis = os_axis;
-    s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
-    s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride; s.nblk_ptr = o.nblk_ptr;
-    for (int i = 0; i < 8; ++i) s.blk_ptr[i] = o.blk_ptr[i];
-    return o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream);
+    // more batch dims than the kernel indexes: the slowest ones are peeled on the host (scattered block pointers move along)
+    return peel_batch_dims(dims, kMaxBatchDims, ie, oe, in, out, o.blk_ptr, o.nblk_ptr, [&](const void* pin, void* pout, const std::vector<BDim>& d2, void* const* blk) -> int {
+        LaunchSpec s;
+        s.core = c; s.in = pin; s.out = pout; s.dims = d2; s.is_axis = is_axis; s.os_axis = os_axis;
+        s.conj_in = o.conj_in; s.conj_out = o.conj_out; s.scale = scale;
+        s.os_blk = o.os_blk; s.os_blk_stride = o.os_blk_stride; s.nblk_ptr = o.nblk_ptr;
+        for (int i = 0; i < 8; ++i) s.blk_ptr[i] = blk ? blk[i] : nullptr;
+        return o.tk == TK_C2C ? launch_c2c<R>(p, s, stream) : launch_real<R>(p, s, stream);
+    });
 }
 
 // byte span [lo, hi) touched by a strided array, relative to its base pointer
@@ -1199,25 +1211,6 @@ static void span_of(int ndim, const size_t* shape, const ptrdiff_t* strides, siz
     *dense = (mx - mn + 1) == count;
 }
 
-#ifndef NDFB_EMU
-struct HostPipe {
-    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-    static constexpr int kMaxChunks = 16;
-    cudaEvent_t ev_in[kMaxChunks], ev_k[kMaxChunks];
-    int device = -1;
-    int init(int dev) {
-        if (device == dev) return 0;
-        for (int i = 0; i < 3; ++i) NDFB_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
-        for (int i = 0; i < kMaxChunks; ++i) {
-            NDFB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-            NDFB_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
-        }
-        device = dev;
-        return 0;
-    }
-};
-static thread_local HostPipe g_pipe;
-
 static bool is_c_order(int ndim, const size_t* shape, const ptrdiff_t* strides) {
     long long expect = 1;
     for (int d = ndim - 1; d >= 0; --d) {
@@ -1227,6 +1220,67 @@ static bool is_c_order(int ndim, const size_t* shape, const ptrdiff_t* strides) 
     return true;
 }
 
+static std::vector<ptrdiff_t> c_strides_of(int ndim, const size_t* shape) {
+    std::vector<ptrdiff_t> st(ndim);
+    long long acc = 1;
+    for (int d = ndim - 1; d >= 0; --d) { st[d] = acc; acc *= (long long)shape[d]; }
+    return st;
+}
+
+// A host array as the device path wants it.  Views with gaps between their elements (slices, steps: the siblings of
+// ndarray's multi_slice_mut / split_at share the allocation) are packed into a private dense C-order buffer, so the
+// library neither reads nor — for outputs — ever WRITES a byte outside the view's logical elements
+// (the reference only touches lane elements, src/lib.rs:119-163).  Dense arrays (any order, any stride signs) are used as they are.
+struct HostArray {
+    const void* user = nullptr;          // caller's pointer (element [0, 0, ...])
+    void* base = nullptr;                // pointer the device path is handed for element [0, 0, ...] (user or packed)
+    std::vector<ptrdiff_t> strides;      // strides matching `base`
+    std::vector<char> packed;            // owns the dense copy when the view has gaps
+    bool is_packed = false;
+    long long lo = 0, hi = 0;            // byte span relative to base
+    void init(const void* ptr, int ndim, const size_t* shape, const ptrdiff_t* st, size_t elem, bool gather) {
+        user = ptr;
+        bool dense;
+        span_of(ndim, shape, st, elem, &lo, &hi, &dense);
+        if (dense) { base = const_cast<void*>(ptr); strides.assign(st, st + ndim); return; }
+        is_packed = true;
+        size_t total = elem;
+        for (int d = 0; d < ndim; ++d) total *= shape[d];
+        packed.resize(total);
+        strides = c_strides_of(ndim, shape);
+        base = packed.data();
+        lo = 0; hi = (long long)total;
+        if (gather) host_nd_copy(true, packed.data(), const_cast<void*>(ptr), ndim, shape, st, elem);
+    }
+    void scatter_back(int ndim, const size_t* shape, const ptrdiff_t* user_strides, size_t elem) {
+        if (is_packed) host_nd_copy(false, packed.data(), const_cast<void*>(user), ndim, shape, user_strides, elem);
+    }
+};
+
+#ifndef NDFB_EMU
+struct HostPipe {
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    static constexpr int kMaxChunks = 16;
+    cudaEvent_t ev_in[kMaxChunks], ev_k[kMaxChunks];
+    int device = -1;
+    StageRing ring;
+    int init(int dev) {
+        if (device != dev) {
+            for (int i = 0; i < 3; ++i) NDFB_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+            for (int i = 0; i < kMaxChunks; ++i) {
+                NDFB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+                NDFB_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+            }
+            device = dev;
+        }
+        return ring.ensure(dev);
+    }
+};
+static thread_local HostPipe g_pipe;
+
+// Large standard-layout host arrays: split along a non-transformed dim and pipeline
+//     [host threads: caller memory -> pinned slot] -> H2D(c) | kernel(c-1) | D2H(c-2) -> [pinned slot -> caller memory]
+// on three streams, so both PCIe directions, the GPU work and the host-side staging copies overlap.
 template <typename R>
 static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale, const void* in, void* out, void* din, void* dout,
                                int ndim, const size_t* shape_in, const ptrdiff_t* strides_in, const size_t* shape_out,
@@ -1249,6 +1303,8 @@ static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale
     if (K < 2 || nd < (size_t)K) return 0;
     int rc = g_pipe.init(p->device);
     if (rc) return rc;
+    StageRing& ring = g_pipe.ring;
+    const bool in_pageable = host_ptr_pageable(in), out_pageable = host_ptr_pageable(out);
     // 2-D copy geometry of one chunk [lo, hi) of dim d:  d == 0: one contiguous range; d == 1 (axis 0): shape[0] rows
     std::vector<size_t> shi(shape_in, shape_in + ndim), sho(shape_out, shape_out + ndim);
     for (int c = 0; c < K; ++c) {
@@ -1259,7 +1315,7 @@ static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale
         const size_t iw = (hi - lo) * (size_t)strides_in[d] * ie, ow = (hi - lo) * (size_t)strides_out[d] * oe;
         const size_t irows = d == 0 ? 1 : shape_in[0], orows = d == 0 ? 1 : shape_out[0];
         const size_t ipitch = d == 0 ? iw : (size_t)strides_in[0] * ie, opitch = d == 0 ? ow : (size_t)strides_out[0] * oe;
-        NDFB_CUDA(cudaMemcpy2DAsync((char*)din + ioff, ipitch, (const char*)in + ioff, ipitch, iw, irows, cudaMemcpyHostToDevice, g_pipe.s[0]));
+        if ((rc = ring.h2d((char*)din + ioff, ipitch, (const char*)in + ioff, ipitch, iw, irows, in_pageable, g_pipe.s[0]))) { cudaDeviceSynchronize(); return rc; }
         NDFB_CUDA(cudaEventRecord(g_pipe.ev_in[c], g_pipe.s[0]));
         NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ev_in[c], 0));
         rc = exec_device<R>(p, o, extra_scale, (const char*)din + ioff, (char*)dout + ooff, ndim, shi.data(), strides_in, sho.data(),
@@ -1267,8 +1323,10 @@ static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale
         if (rc) { cudaDeviceSynchronize(); return rc; }
         NDFB_CUDA(cudaEventRecord(g_pipe.ev_k[c], g_pipe.s[1]));
         NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[2], g_pipe.ev_k[c], 0));
-        NDFB_CUDA(cudaMemcpy2DAsync((char*)out + ooff, opitch, (const char*)dout + ooff, opitch, ow, orows, cudaMemcpyDeviceToHost, g_pipe.s[2]));
+        if ((rc = ring.d2h((char*)out + ooff, opitch, (const char*)dout + ooff, opitch, ow, orows, out_pageable, g_pipe.s[2]))) { cudaDeviceSynchronize(); return rc; }
+        if ((rc = ring.drain(false))) { cudaDeviceSynchronize(); return rc; }
     }
+    if ((rc = ring.drain(true))) return rc;
     NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[2]));
     *done = 1;
     return 0;
@@ -1286,12 +1344,15 @@ static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const voi
         g_pool.end_call();
         return rc;
     }
-    // host arrays: move the touched byte spans through device staging buffers, strides unchanged
+    // host arrays: dense views move as their byte span (strides unchanged), views with gaps as packed logical elements
     const size_t ie = (o.in_complex ? 2 : 1) * sizeof(R), oe = (o.out_complex ? 2 : 1) * sizeof(R);
-    long long ilo, ihi, olo, ohi;
-    bool idense, odense;
-    span_of(ndim, shape_in, strides_in, ie, &ilo, &ihi, &idense);
-    span_of(ndim, shape_out, strides_out, oe, &olo, &ohi, &odense);
+    for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) return 0;
+    HostArray hi_, ho_;
+    hi_.init(in, ndim, shape_in, strides_in, ie, /*gather=*/true);
+    ho_.init(out, ndim, shape_out, strides_out, oe, /*gather=*/false);
+    const ptrdiff_t* si = hi_.strides.data();
+    const ptrdiff_t* so = ho_.strides.data();
+    const long long ilo = hi_.lo, ihi = hi_.hi, olo = ho_.lo, ohi = ho_.hi;
     if (ihi == ilo || ohi == olo) return 0;
     int rc = dev_set(p->device);
     if (rc) return rc;
@@ -1299,24 +1360,20 @@ static int exec_any(ndfb_plan* p, const OpInfo& o, double extra_scale, const voi
     if ((rc = g_pool.get(0, p->device, (size_t)(ihi - ilo), &din))) return rc;
     if ((rc = g_pool.get(1, p->device, (size_t)(ohi - olo), &dout))) return rc;
 #ifndef NDFB_EMU
-    // Large standard-layout arrays: split along a non-transformed dim and pipeline H2D(c+1) | kernel(c) | D2H(c-1)
-    // on three streams, so the two PCIe directions and the GPU work overlap (the array is 2 x 512 MiB for c2).
     {
         int done = 0;
-        rc = exec_host_pipelined<R>(p, o, extra_scale, in, out, din, dout, ndim, shape_in, strides_in, shape_out, strides_out,
-                                    axis, ie, oe, &done);
-        if (rc || done) return rc;
+        rc = exec_host_pipelined<R>(p, o, extra_scale, hi_.base, ho_.base, din, dout, ndim, shape_in, si, shape_out, so, axis, ie, oe, &done);
+        if (rc) return rc;
+        if (done) { ho_.scatter_back(ndim, shape_out, strides_out, oe); return 0; }
     }
 #endif
-    if ((rc = dev_h2d(din, (const char*)in + ilo, (size_t)(ihi - ilo), stream))) return rc;
-    if (!odense) {  // keep the bytes between output elements intact
-        if ((rc = dev_h2d(dout, (const char*)out + olo, (size_t)(ohi - olo), stream))) return rc;
-    }
-    rc = exec_device<R>(p, o, extra_scale, (const char*)din - ilo, (char*)dout - olo, ndim, shape_in, strides_in,
-                        shape_out, strides_out, axis, stream);
+    if ((rc = dev_h2d(din, (const char*)hi_.base + ilo, (size_t)(ihi - ilo), stream))) return rc;
+    rc = exec_device<R>(p, o, extra_scale, (const char*)din - ilo, (char*)dout - olo, ndim, shape_in, si, shape_out, so, axis, stream);
     if (rc) return rc;
-    if ((rc = dev_d2h((char*)out + olo, dout, (size_t)(ohi - olo), stream))) return rc;
-    return dev_sync(stream);
+    if ((rc = dev_d2h((char*)ho_.base + olo, dout, (size_t)(ohi - olo), stream))) return rc;
+    if ((rc = dev_sync(stream))) return rc;
+    ho_.scatter_back(ndim, shape_out, strides_out, oe);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1416,6 +1473,8 @@ static int chain_host_pipelined(const std::vector<ChainStep>& st, const void* hi
     ndfb_plan* p = st[0].p;
     int rc = g_pipe.init(p->device);
     if (rc) return rc;
+    StageRing& ring = g_pipe.ring;
+    const bool in_pageable = host_ptr_pageable(hin), out_pageable = host_ptr_pageable(hout);
     // first step, piece by piece behind the upload
     ChainView d1;
     if ((rc = chain_dst<R>(st, 0, din, &d1, dout, p->device))) return rc;
@@ -1427,7 +1486,7 @@ static int chain_host_pipelined(const std::vector<ChainStep>& st, const void* hi
             const size_t lo = nd * c / K0, hi = nd * (c + 1) / K0;
             if (hi == lo) continue;
             const ChunkGeom g = chunk_geom(din, d0, lo, hi, ie);
-            NDFB_CUDA(cudaMemcpy2DAsync((char*)din.ptr + g.off, g.pitch, (const char*)hin + g.off, g.pitch, g.width, g.rows, cudaMemcpyHostToDevice, g_pipe.s[0]));
+            if ((rc = ring.h2d((char*)din.ptr + g.off, g.pitch, (const char*)hin + g.off, g.pitch, g.width, g.rows, in_pageable, g_pipe.s[0]))) { cudaDeviceSynchronize(); return rc; }
             NDFB_CUDA(cudaEventRecord(g_pipe.ev_in[c], g_pipe.s[0]));
             NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ev_in[c], 0));
             a.shape[d0] = b.shape[d0] = hi - lo;
@@ -1455,9 +1514,11 @@ static int chain_host_pipelined(const std::vector<ChainStep>& st, const void* hi
             if (rc) { cudaDeviceSynchronize(); return rc; }
             NDFB_CUDA(cudaEventRecord(g_pipe.ev_k[c], g_pipe.s[1]));
             NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[2], g_pipe.ev_k[c], 0));
-            NDFB_CUDA(cudaMemcpy2DAsync((char*)hout + g.off, g.pitch, (const char*)dout.ptr + g.off, g.pitch, g.width, g.rows, cudaMemcpyDeviceToHost, g_pipe.s[2]));
+            if ((rc = ring.d2h((char*)hout + g.off, g.pitch, (const char*)dout.ptr + g.off, g.pitch, g.width, g.rows, out_pageable, g_pipe.s[2]))) { cudaDeviceSynchronize(); return rc; }
+            if ((rc = ring.drain(false))) { cudaDeviceSynchronize(); return rc; }
         }
     }
+    if ((rc = ring.drain(true))) return rc;
     NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[2]));
     NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[1]));
     *done = 1;
@@ -1483,10 +1544,12 @@ static int chain_any(const std::vector<ChainStep>& st, const void* in, void* out
         return rc;
     }
     const size_t ie = (st.front().o.in_complex ? 2 : 1) * sizeof(R), oe = (st.back().o.out_complex ? 2 : 1) * sizeof(R);
-    long long ilo, ihi, olo, ohi;
-    bool idense, odense;
-    span_of(ndim, shape_in, strides_in, ie, &ilo, &ihi, &idense);
-    span_of(ndim, shape_out, strides_out, oe, &olo, &ohi, &odense);
+    for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) return 0;
+    HostArray hi_, ho_;   // views with gaps travel as packed logical elements (see exec_any)
+    hi_.init(in, ndim, shape_in, strides_in, ie, /*gather=*/true);
+    ho_.init(out, ndim, shape_out, strides_out, oe, /*gather=*/false);
+    vi.strides = hi_.strides; vo.strides = ho_.strides;
+    const long long ilo = hi_.lo, ihi = hi_.hi, olo = ho_.lo, ohi = ho_.hi;
     if (ihi == ilo || ohi == olo) return 0;
     void *din = nullptr, *dout = nullptr;
     if ((rc = g_pool.get(0, p->device, (size_t)(ihi - ilo), &din))) return rc;
@@ -1495,15 +1558,17 @@ static int chain_any(const std::vector<ChainStep>& st, const void* in, void* out
 #ifndef NDFB_EMU
     {
         int done = 0;
-        rc = chain_host_pipelined<R>(st, in, out, vi, vo, ie, oe, &done);
-        if (rc || done) return rc;
+        rc = chain_host_pipelined<R>(st, hi_.base, ho_.base, vi, vo, ie, oe, &done);
+        if (rc) return rc;
+        if (done) { ho_.scatter_back(ndim, shape_out, strides_out, oe); return 0; }
     }
 #endif
-    if ((rc = dev_h2d(din, (const char*)in + ilo, (size_t)(ihi - ilo), stream))) return rc;
-    if (!odense && (rc = dev_h2d(dout, (const char*)out + olo, (size_t)(ohi - olo), stream))) return rc;
+    if ((rc = dev_h2d(din, (const char*)hi_.base + ilo, (size_t)(ihi - ilo), stream))) return rc;
     if ((rc = chain_device<R>(st, vi, vo, stream))) return rc;
-    if ((rc = dev_d2h((char*)out + olo, dout, (size_t)(ohi - olo), stream))) return rc;
-    return dev_sync(stream);
+    if ((rc = dev_d2h((char*)ho_.base + olo, dout, (size_t)(ohi - olo), stream))) return rc;
+    if ((rc = dev_sync(stream))) return rc;
+    ho_.scatter_back(ndim, shape_out, strides_out, oe);
+    return 0;
 }
 
 }  // namespace ndfb
@@ -1708,6 +1773,11 @@ void ndfb_hint_next_launch_smem(size_t bytes) { launch_smem_floor() = bytes; }
 const char* ndfb_last_error(void) { return g_err.c_str(); }
 const char* ndfb_version(void) { return version_string(); }
 uint64_t ndfb_launch_count(void) { return g_launches.load(); }
-void ndfb_release_workspaces(void) { g_pool.release(); }
+void ndfb_release_workspaces(void) {
+    g_pool.release();
+#ifndef NDFB_EMU
+    g_pipe.ring.release();
+#endif
+}
 
 }  // extern "C"

@@ -237,7 +237,15 @@ def test_rsfft_unaligned_rows_fall_back(hs, capfd):
     y = np.zeros((4, 65), complex); yo = np.zeros((4, 65), complex)
     os.environ["NDFB_TRACE"] = "1"
     try:
-        be.ndfft_r2c(x, y, be.R2cFftHandler(128), 1)
+        # through the DEVICE entry (the emulation build's "device" memory is host memory): host views with gaps are packed
+        # into an aligned staging copy by the library, so only device views can present an odd element offset
+        import ctypes
+        from ndrustfft_b200 import _lib
+        h = be.R2cFftHandler(128)
+        SZ, PD = ctypes.c_size_t * 2, ctypes.c_ssize_t * 2
+        rc = be.lib.dll.ndfb_exec(h._plan, _lib.OP_R2C, _lib.NORM_DEFAULT, ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(y.ctypes.data), 2,
+                                  SZ(4, 128), PD(129, 1), SZ(4, 65), PD(65, 1), 1, _lib.MEM_DEVICE, None)
+        be.lib.check(rc)
     finally:
         del os.environ["NDFB_TRACE"]
     orc.ndfft_r2c(np.ascontiguousarray(x), yo, orc.R2cFftHandler(128), 1)
