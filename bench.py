@@ -1,30 +1,30 @@
 #!/usr/bin/env python3
-"""bench.py — BASELINE.json config c2: 2-D complex f32 ndfft/ndifft along both axes of 8192 x 8192.
+"""bench.py — axis-transform hot path of ndrustfft on B200.
 
-One STEP = the four axis transforms of that config on one synthetic array, all through the public API
-(ndrustfft_b200.ndfft / ndifft  ->  C ABI  ->  sm_100a kernels):
-
-    ndfft  axis 1 (contiguous rows, path A)      x -> a
-    ndfft  axis 0 (stride 8192 elements, path B) a -> b
-    ndifft axis 0                                b -> a
-    ndifft axis 1                                a -> b     (b == x up to rounding)
-
-`value`   whole-job GFLOP/s (5 N log2 N per lane), inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     the same step through the HOST-array path of the C ABI (pinned numpy arrays in, pinned numpy arrays
-          out): H2D + kernel + D2H inside the timed region, every call.
-`roofline` for the slowest of the four launches: algorithmic bytes (input once + output once = 1 GiB) / its
-          CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline` / `--impl reference`: the reference's CPU path cannot be built here (Rust + un-vendored crates, no
-          toolchain), so the oracle port (scipy.fft/pocketfft over lanes, all host threads — what `_par` does with
-          rayon) is timed on a bounded lane sample of the same workload.  kind = "port".
-
-N > 1 (torchrun): lanes are independent (src/lib.rs:120-124), so each rank transforms its own 8192 x 8192 array
-with no collective on the data path — "scaling": "weak".
+HEADLINE WORKLOAD (every N): BASELINE.json config c3, the 512^3 f64 real 3-D spectral transform
+    ndfft_r2c axis 2  ->  ndfft axis 1  ->  [slab exchange, N > 1]  ->  ndfft axis 0          (examples/rfft2.rs:29-33 pattern)
+It is the one config the north_star gives a multi-GPU target for, and the driver derives scaling efficiency from the
+per-N `value`s of this file, so the same global transform is timed at N = 1, 2, 4, 8: "scaling": "strong".
+  N = 1   three launches on one GPU (ndrustfft_b200.dist.SlabR2cFft3d with one rank = r2c, axis-1, axis-0 pass).
+  N > 1   axis-0 slabs per rank, the axis-1 pass's stores ARE the all-to-all (peer-mapped receive buffers over NVLink,
+          ndfb_exec_scatter_out), then the axis-0 pass on the rank's axis-1 slab; device time, max over ranks.
+`value`        GFLOP/s of the ONE global transform (2.5 n log2 n per real lane, 5 n log2 n per complex lane = 9.08e9).
+`e2e`          the same transform from PAGEABLE host arrays (plain np.empty, what ndarray's as_ptr() hands the shim):
+               N = 1 one ndfb_exec_chain(mem=HOST) call per step; N > 1 every rank uploads its slab, transforms, downloads.
+`roofline`     the dominant kernel of the step (largest share of the device time) at N = 1; at N > 1 also the NVLink side.
+`configs`      (N = 1) every other BASELINE config, per call: c1 (incl. the criterion ramp of benches/ndrustfft.rs:9-60 and
+               a CUDA-graph replay), c2 (4 calls + the step-weighted fraction), c3 stages, c4 (8 calls), c5a, c5b — each
+               with ms, GB/s of algorithmic bytes, fraction of the measured HBM peak, GFLOP/s and the scipy CPU stand-in.
+`c2_weak`      (N > 1) round 1's headline (four axis transforms of one 8192^2 c64 array per rank, no collective).
+`cpu_baseline` / `--impl reference`: ndrustfft cannot be built here (Rust; rustfft/realfft/rustdct not vendored; the
+               harness probes `cargo --version` and says so), so the oracle port (scipy.fft/pocketfft, all host threads =
+               what `_par` does with rayon) runs the same three axis passes on the full 512^3 array.  kind = "port".
 """
 import argparse
 import json
 import math
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -34,11 +34,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_AXIS = 8192
-FLOPS_PER_TRANSFORM = N_AXIS * 5.0 * N_AXIS * math.log2(N_AXIS)   # 8192 lanes x 5 n log2 n = 4.362e9
-BYTES_PER_TRANSFORM = 2 * N_AXIS * N_AXIS * 8                      # read once + write once = 1 GiB
-STEP_NAMES = ["ndfft axis1 (contiguous)", "ndfft axis0 (strided)", "ndifft axis0 (strided)", "ndifft axis1 (contiguous)"]
-METRIC = "GFLOP/s (5*N*log2N) per axis transform, c2: 8192x8192 c64 ndfft/ndifft both axes"
+N3 = 512
+M3 = N3 // 2 + 1
+C3_FLOPS = N3 * N3 * 2.5 * N3 * math.log2(N3) + 2 * N3 * M3 * 5.0 * N3 * math.log2(N3)      # 9.084e9
+C3_STAGE_BYTES = [N3 ** 3 * 8 + N3 * N3 * M3 * 16, 2 * N3 * N3 * M3 * 16, 2 * N3 * N3 * M3 * 16]
+C3_STAGE_FLOPS = [N3 * N3 * 2.5 * N3 * math.log2(N3), N3 * M3 * 5.0 * N3 * math.log2(N3), N3 * M3 * 5.0 * N3 * math.log2(N3)]
+C3_STAGE_NAMES = ["ndfft_r2c axis2 512^3 f64 -> 512x512x257 c128", "ndfft axis1 512x512x257 c128", "ndfft axis0 512x512x257 c128"]
+METRIC = "GFLOP/s (2.5 n log2 n real / 5 n log2 n complex lanes) of the 512^3 f64 real 3-D transform (c3: ndfft_r2c + 2 x ndfft)"
+
+
+def config_of(n_gpus):
+    return {"workload": "c3: 512^3 f64 real 3-D spectral transform = ndfft_r2c axis 2, ndfft axis 1, ndfft axis 0 (one step = the three axis passes of ONE global array)",
+            "shape": [N3, N3, N3], "l2": "inputs larger than L2 (1 GiB real input, 1.08 GB complex spectrum)",
+            "decomposition": "single GPU" if n_gpus == 1 else f"axis-0 slabs over {n_gpus} ranks, one exchange to axis-1 slabs before the last pass"}
 
 
 def measured_peak():
@@ -49,6 +57,25 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cargo_probe():
+    """the intended CPU arm is ndrustfft's own criterion benches; needs a Rust toolchain AND the crates."""
+    exe = shutil.which("cargo")
+    if not exe:
+        return {"cargo": None, "note": "no cargo/rustc in this image: ndrustfft (rustfft 6.1 / realfft 3.2 / rustdct 0.7, not vendored) cannot be built; CPU arm = oracle port over scipy.fft"}
+    try:
+        v = subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=10).stdout.strip()
+    except Exception as e:  # pragma: no cover
+        v = repr(e)
+    return {"cargo": v, "note": "cargo present, but the reference's crates are not vendored and there is no network: still the oracle port"}
 
 
 class ClockSampler:
@@ -63,7 +90,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,7 +104,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -100,48 +127,63 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_run(steps, warmup, sample_lanes=1024):
-    """The oracle port on host cores: scipy.fft over a bounded lane sample of the c2 step (all threads)."""
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (scipy.fft over lanes, all host threads) on the same workload
+# ------------------------------------------------------------------------------------------------------
+def cpu_c3_step_factory(frac=1.0):
+    """One c3 step on the host: r2c axis 2, fft axis 1, fft axis 0 of a (512*frac, 512, 512) slab... frac < 1 keeps the
+    lane LENGTHS (512 on every axis) and cuts the lane COUNT: axes 2 and 1 run on n0*frac planes, axis 0 on n1*frac columns."""
     import numpy as np
     from oracle import ndrustfft_oracle as orc
-    orc.set_native_precision(True)   # time complex64 arithmetic, as rustfft on Complex<f32> would
-    cores = os.cpu_count() or 1
-    rng = np.random.default_rng(0xB200 + 32)
-    rows = (rng.uniform(-1, 1, (sample_lanes, N_AXIS)) + 1j * rng.uniform(-1, 1, (sample_lanes, N_AXIS))).astype(np.complex64)
-    cols = np.ascontiguousarray(rows.T)            # (8192, sample) : axis-0 lanes with stride = sample elements
-    h = orc.FftHandler(N_AXIS, np.float32)
-    ra, ca = np.empty_like(rows), np.empty_like(cols)
-    rb, cb = np.empty_like(rows), np.empty_like(cols)
+    rng = np.random.default_rng(0xB200 + 48)
+    p0 = max(1, int(round(N3 * frac)))
+    x = rng.uniform(-1, 1, (p0, N3, N3))
+    a = np.empty((p0, N3, M3), np.complex128)
+    b = np.empty_like(a)
+    c_in = np.empty((N3, p0, M3), np.complex128)
+    c_in[...] = 0.5
+    c_out = np.empty_like(c_in)
+    hr, hc = orc.R2cFftHandler(N3), orc.FftHandler(N3)
 
     def step():
-        orc.ndfft_par(rows, ra, h, 1)
-        orc.ndfft_par(cols, ca, h, 0)
-        orc.ndifft_par(ca, cb, h, 0)
-        orc.ndifft_par(ra, rb, h, 1)
+        orc.ndfft_r2c_par(x, a, hr, 2)
+        orc.ndfft_par(a, b, hc, 1)
+        orc.ndfft_par(c_in, c_out, hc, 0)
 
-    for _ in range(warmup):
+    return step, C3_FLOPS * p0 / N3, p0
+
+
+def cpu_c3_run(steps, warmup, budget_s=150.0):
+    cores = host_threads()
+    step, flops, p0 = cpu_c3_step_factory(1.0)
+    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
+    if first * (steps + warmup) > budget_s:          # bounded sample: a quarter of the lanes of every pass
+        step, flops, p0 = cpu_c3_step_factory(0.25)
+        step()
+    for _ in range(max(0, warmup - 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    flops = 4 * sample_lanes * 5.0 * N_AXIS * math.log2(N_AXIS)
-    return flops / dt / 1e9, dt, cores, f"{sample_lanes} of 8192 lanes per transform (4 transforms/step), scipy.fft complex64, workers={cores}"
+    sample = (f"full 512^3 array ({p0} of 512 planes per pass)" if p0 == N3 else f"{p0} of 512 planes per pass (lane lengths unchanged)") + \
+        f", scipy.fft (pocketfft) f64, workers={cores}"
+    return flops / dt / 1e9, dt, cores, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, args.steps)
-    gf, dt, cores, sample = cpu_port_run(steps, max(1, min(args.warmup, 3)))
+    K, W = max(1, args.steps), max(0, args.warmup)
+    gf, dt, cores, sample = cpu_c3_run(K, W)
     line = {
-        "impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: 8192x8192 c64 ndfft axis1, ndfft axis0, ndifft axis0, ndifft axis1 (bounded lane sample)"},
+        "impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_of(args.gpus),
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "ndrustfft itself is not buildable in this image (no rustc/cargo, crates not vendored); oracle port = scipy.fft over lanes"},
+                         "note": "ndrustfft itself is not buildable in this image; oracle port = scipy.fft over lanes with all host threads (what `_par` does with rayon)",
+                         "toolchain": cargo_probe()},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -149,13 +191,271 @@ def run_reference(args):
     return 0
 
 
-# per-launch DRAM traffic of the two bench kernels from `ncu --set full` captures of this same command (profiles/)
-ROWS_TRAFFIC = 1.028e9
-ROWS_TRAFFIC_SRC = "ncu --set full, profiles/r1z_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 491 MB per launch"
-COLS2_TRAFFIC = 2.05e9
-COLS2_TRAFFIC_SRC = "ncu, profiles/r1l_ncu_bench_summary.txt + r1t l2 probe: 537 MB read + 488-492 MB written per pass kernel, two pass kernels per call"
-COLS_TRAFFIC = 1.130e9
-COLS_TRAFFIC_SRC = "ncu --set full, profiles/r1z_ncu_bench_summary.txt: dram__bytes_read 537 MB + dram__bytes_write 593 MB per launch (both passes; the intermediate stays in L2)"
+# ------------------------------------------------------------------------------------------------------
+# per-config measurements (N = 1): device-resident, CUDA events, median of `iters`
+# ------------------------------------------------------------------------------------------------------
+class ConfigBench:
+    def __init__(self, nb, torch, np, peak, iters, cpu):
+        self.nb, self.torch, self.np, self.peak, self.iters, self.cpu = nb, torch, np, peak, iters, cpu
+        self.flush_buf = None
+        self.rows = []
+
+    def flush(self):
+        if self.flush_buf is None:
+            self.flush_buf = self.torch.empty(256 << 20, dtype=self.torch.uint8, device="cuda")
+        self.flush_buf.zero_()
+
+    def time_call(self, fn, iters=None, flush=False):
+        t = self.torch
+        for _ in range(3):
+            fn()
+        t.cuda.synchronize()
+        ts = []
+        for _ in range(iters or self.iters):
+            if flush:
+                self.flush()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            t.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2], ts[0]
+
+    def rnd(self, shape, dt, cx):
+        t = self.torch
+        rt = t.float32 if dt == self.np.float32 else t.float64
+        if cx:
+            return t.complex(t.rand(shape, device="cuda", dtype=rt) * 2 - 1, t.rand(shape, device="cuda", dtype=rt) * 2 - 1)
+        return t.rand(shape, device="cuda", dtype=rt) * 2 - 1
+
+    def cpu_time(self, fn, flops, reps=1):
+        if not self.cpu:
+            return None
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dt = (time.perf_counter() - t0) / reps
+        return {"ms": round(dt * 1e3, 3), "GFLOP/s": round(flops / dt / 1e9, 2)}
+
+    def add(self, cfg, call, dtype, ms, ms_min, nbytes, flops, cpu=None, **extra):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        row = {"cfg": cfg, "call": call, "dtype": dtype, "ms": round(ms, 5), "ms_min": round(ms_min, 5), "GB/s": round(gbs, 1),
+               "frac": round(gbs / self.peak, 4), "GFLOP/s": round(flops / (ms * 1e-3) / 1e9, 1)}
+        if cpu:
+            row["cpu"] = cpu
+        row.update(extra)
+        self.rows.append(row)
+        return row
+
+    # ---- c1: 128 x 128 f64, the reference's own bench shape (launch-latency bound) ----
+    def c1(self):
+        nb, np, t = self.nb, self.np, self.torch
+        from oracle import ndrustfft_oracle as orc
+        n = 128
+        xc = self.rnd((n, n), np.float64, True); yc = t.empty_like(xc)
+        xr = self.rnd((n, n), np.float64, False); yr = t.empty_like(xr)
+        hc, hr, hd = nb.FftHandler(n), nb.R2cFftHandler(n), nb.DctHandler(n)
+        xc_h, xr_h = xc.cpu().numpy(), xr.cpu().numpy()
+        oc, orr, od = orc.FftHandler(n), orc.R2cFftHandler(n), orc.DctHandler(n)
+        fl_c, fl_r = n * 5.0 * n * math.log2(n), n * 2.5 * n * math.log2(n)
+        for ax in (0, 1):
+            so = [n, n]; so[ax] = n // 2 + 1
+            yh = t.empty(so, dtype=t.complex128, device="cuda")
+            cases = [("ndfft", lambda: nb.ndfft(xc, yc, hc, ax), 2 * n * n * 16, fl_c, lambda: orc.ndfft(xc_h, np.empty_like(xc_h), oc, ax)),
+                     ("ndfft_r2c", lambda: nb.ndfft_r2c(xr, yh, hr, ax), n * n * 8 + yh.numel() * 16, fl_r,
+                      lambda: orc.ndfft_r2c(xr_h, np.empty(so, np.complex128), orr, ax)),
+                     ("nddct2", lambda: nb.nddct2(xr, yr, hd, ax), 2 * n * n * 8, fl_r, lambda: orc.nddct2(xr_h, np.empty_like(xr_h), od, ax))]
+            for name, fn, nbytes, fl, cfn in cases:
+                med, mn = self.time_call(fn, flush=True)
+                # the same call replayed 200x from one CUDA graph: the per-call cost without host launch overhead
+                g = t.cuda.CUDAGraph()
+                side = t.cuda.Stream()
+                side.wait_stream(t.cuda.current_stream())
+                with t.cuda.stream(side):
+                    fn()
+                    with t.cuda.graph(g, stream=side):
+                        for _ in range(200):
+                            fn()
+                t.cuda.current_stream().wait_stream(side)
+                g.replay(); t.cuda.synchronize()
+                e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                e0.record(); g.replay(); e1.record(); t.cuda.synchronize()
+                graph_us = e0.elapsed_time(e1) * 1e3 / 200
+                self.add("c1", f"{name} axis{ax} 128x128 f64", "f64", med, mn, nbytes, fl, cpu=self.cpu_time(cfn, fl, reps=20),
+                         us_per_call_in_cuda_graph=round(graph_us, 3), note="launch-latency bound: 0.04-0.08 us of HBM time")
+        # host-array calls (what a Rust caller with ndarray memory pays per call: two PCIe copies + launch)
+        xh = np.ascontiguousarray(xc_h); yh = np.empty_like(xh)
+        nb.ndfft(xh, yh, hc, 0)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            nb.ndfft(xh, yh, hc, 0)
+        self.rows.append({"cfg": "c1", "call": "ndfft axis0 128x128 c128 through ndfb_exec(mem=HOST), pageable numpy arrays",
+                          "dtype": "f64", "us_per_call_host": round((time.perf_counter() - t0) / 50 * 1e6, 2)})
+        # criterion ramp of the reference's benches (benches/ndrustfft.rs:9-60): n x n f64, axis 0; DCT-I at 2^k + 1
+        for n in (128, 264, 512, 1024):
+            x = self.rnd((n, n), np.float64, True); y = t.empty_like(x)
+            h = nb.FftHandler(n)
+            med, mn = self.time_call(lambda: nb.ndfft(x, y, h, 0), flush=True)
+            xh_ = x.cpu().numpy(); oh = orc.FftHandler(n)
+            fl = n * 5.0 * n * math.log2(n)
+            self.add("c1-ramp", f"ndfft axis0 {n}x{n} c128", "f64", med, mn, 2 * n * n * 16, fl,
+                     cpu=self.cpu_time(lambda: orc.ndfft(xh_, np.empty_like(xh_), oh, 0), fl, reps=5))
+            nd = n + 1
+            xr_ = self.rnd((nd, nd), np.float64, False); yr_ = t.empty_like(xr_)
+            hd_ = nb.DctHandler(nd)
+            med, mn = self.time_call(lambda: nb.nddct1(xr_, yr_, hd_, 0), flush=True)
+            xrh = xr_.cpu().numpy(); odh = orc.DctHandler(nd)
+            fl = nd * 2.5 * nd * math.log2(nd)
+            self.add("c1-ramp", f"nddct1 axis0 {nd}x{nd} f64", "f64", med, mn, 2 * nd * nd * 8, fl,
+                     cpu=self.cpu_time(lambda: orc.nddct1(xrh, np.empty_like(xrh), odh, 0), fl, reps=5))
+
+    # ---- c2: 8192 x 8192 c64, both axes, forward and inverse ----
+    def c2(self):
+        nb, np, t = self.nb, self.np, self.torch
+        from oracle import ndrustfft_oracle as orc
+        n = 8192
+        x = self.rnd((n, n), np.float32, True); a = t.empty_like(x); b = t.empty_like(x)
+        h = nb.FftHandler(n, np.float32)
+        fl, nbytes = n * 5.0 * n * math.log2(n), 2 * n * n * 8
+        cpu = {}
+        if self.cpu:
+            orc.set_native_precision(True)
+            xh = x.cpu().numpy(); yh = np.empty_like(xh); oh = orc.FftHandler(n, np.float32)
+            for ax in (1, 0):
+                cpu[ax] = self.cpu_time(lambda: orc.ndfft_par(xh, yh, oh, ax), fl)
+            orc.set_native_precision(False)
+            del xh, yh
+        calls = [("ndfft axis1 (contiguous)", lambda: nb.ndfft(x, a, h, 1), 1), ("ndfft axis0 (strided)", lambda: nb.ndfft(a, b, h, 0), 0),
+                 ("ndifft axis0 (strided)", lambda: nb.ndifft(b, a, h, 0), 0), ("ndifft axis1 (contiguous)", lambda: nb.ndifft(a, b, h, 1), 1)]
+        tot = 0.0
+        for name, fn, ax in calls:
+            med, mn = self.time_call(fn)
+            tot += med
+            self.add("c2", f"{name} 8192x8192 c64", "f32", med, mn, nbytes, fl, cpu=cpu.get(ax))
+        rel = (t.linalg.vector_norm(b - x) / t.linalg.vector_norm(x)).item()
+        assert rel < 1e-5, rel
+        self.rows.append({"cfg": "c2", "call": "step = the four calls above", "dtype": "f32", "ms": round(tot, 5),
+                          "GFLOP/s": round(4 * fl / (tot * 1e-3) / 1e9, 1), "step_weighted_frac": round(4 * nbytes / (tot * 1e-3) / 1e9 / self.peak, 4),
+                          "roundtrip_rel_l2": rel})
+        del x, a, b
+
+    # ---- c3 stages through the public single calls (unpadded arrays), forward and the inverse r2c ----
+    def c3(self):
+        nb, np, t = self.nb, self.np, self.torch
+        n = N3
+        x = self.rnd((n, n, n), np.float64, False)
+        a1 = t.empty((n, n, M3), dtype=t.complex128, device="cuda"); a2 = t.empty_like(a1)
+        hr, hc = nb.R2cFftHandler(n), nb.FftHandler(n)
+        for name, fn, nbytes, fl in (
+                ("ndfft_r2c axis2 512^3 f64", lambda: nb.ndfft_r2c(x, a1, hr, 2), C3_STAGE_BYTES[0], C3_STAGE_FLOPS[0]),
+                ("ndfft axis1 512x512x257 c128", lambda: nb.ndfft(a1, a2, hc, 1), C3_STAGE_BYTES[1], C3_STAGE_FLOPS[1]),
+                ("ndfft axis0 512x512x257 c128", lambda: nb.ndfft(a2, a1, hc, 0), C3_STAGE_BYTES[2], C3_STAGE_FLOPS[2]),
+                ("ndifft axis0 512x512x257 c128", lambda: nb.ndifft(a1, a2, hc, 0), C3_STAGE_BYTES[2], C3_STAGE_FLOPS[2]),
+                ("ndifft_r2c axis2 512^3 f64", lambda: nb.ndifft_r2c(a1, x, hr, 2), C3_STAGE_BYTES[0], C3_STAGE_FLOPS[0])):
+            med, mn = self.time_call(fn)
+            self.add("c3", name, "f64", med, mn, nbytes, fl)
+        del x, a1, a2
+
+    # ---- c4: DCT-I..IV on 4096 x 4096 f64, both axes ----
+    def c4(self):
+        nb, np, t = self.nb, self.np, self.torch
+        from oracle import ndrustfft_oracle as orc
+        n = 4096
+        x = self.rnd((n, n), np.float64, False); y = t.empty_like(x); z = t.empty_like(x)
+        h = nb.DctHandler(n)
+        fl, nbytes = n * 2.5 * n * math.log2(n), 2 * n * n * 8
+        xh = x.cpu().numpy() if self.cpu else None
+        oh = orc.DctHandler(n)
+        for ax in (1, 0):
+            for k in (1, 2, 3, 4):
+                f = getattr(nb, f"nddct{k}")
+                med, mn = self.time_call(lambda: f(x, y, h, ax))
+                cpu = self.cpu_time(lambda: getattr(orc, f"nddct{k}_par")(xh, np.empty_like(xh), oh, ax), fl) if self.cpu else None
+                self.add("c4", f"nddct{k} axis{ax} 4096x4096 f64", "f64", med, mn, nbytes, fl, cpu=cpu)
+            nb.nddct2(x, y, h, ax); nb.nddct3(y, z, h, ax)       # Chebyshev round trip: dct3(dct2(x)) = 2n x
+            rel = (t.linalg.vector_norm(z / (2.0 * n) - x) / t.linalg.vector_norm(x)).item()
+            assert rel < 1e-12, rel
+        del x, y, z
+
+    # ---- c5a: 360 x 1000 x 384 c128, every axis ----
+    def c5a(self):
+        nb, np, t = self.nb, self.np, self.torch
+        from oracle import ndrustfft_oracle as orc
+        shape = (360, 1000, 384)
+        x = self.rnd(shape, np.float64, True); y = t.empty_like(x)
+        for ax in (0, 1, 2):
+            n = shape[ax]
+            h = nb.FftHandler(n)
+            lanes = x.numel() // n
+            fl = lanes * 5.0 * n * math.log2(n)
+            cpu = None
+            if self.cpu:   # a quarter of the lanes (cut along another axis), lane length unchanged
+                cut = [slice(None)] * 3
+                cut[(ax + 1) % 3] = slice(0, shape[(ax + 1) % 3] // 4)
+                xs = np.ascontiguousarray(x[tuple(cut)].cpu().numpy()); ys = np.empty_like(xs); oh = orc.FftHandler(n)
+                cpu = self.cpu_time(lambda: orc.ndfft_par(xs, ys, oh, ax), fl / 4)
+                cpu["sample"] = "1/4 of the lanes"
+                del xs, ys
+            for nm, f in (("ndfft", nb.ndfft), ("ndifft", nb.ndifft)):
+                med, mn = self.time_call(lambda: f(x, y, h, ax), iters=max(3, self.iters // 2))
+                self.add("c5a", f"{nm} axis{ax} n={n} 360x1000x384 c128", "f64", med, mn, 2 * x.numel() * 16, fl, cpu=cpu if nm == "ndfft" else None)
+        del x, y
+        # the shape above never needs Bluestein: a 1009-point (prime) axis of a comparable array
+        x = self.rnd((1009, 4096), np.float64, True); y = t.empty_like(x)
+        h = nb.FftHandler(1009)
+        med, mn = self.time_call(lambda: nb.ndfft(x, y, h, 0), iters=max(3, self.iters // 2))
+        self.add("c5a+", "ndfft axis0 n=1009 (prime: fused Bluestein) 1009x4096 c128", "f64", med, mn, 2 * x.numel() * 16, 4096 * 5.0 * 1009 * math.log2(1009))
+        del x, y
+
+    # ---- c5b: 2^24-point rows, batch 64, c64 (four-step: two HBM passes) ----
+    def c5b(self):
+        nb, np, t = self.nb, self.np, self.torch
+        from oracle import ndrustfft_oracle as orc
+        n, b = 1 << 24, 64
+        x = self.rnd((b, n), np.float32, True); y = t.empty_like(x)
+        h = nb.FftHandler(n, np.float32)
+        fl = b * 5.0 * n * 24
+        cpu = None
+        if self.cpu:
+            orc.set_native_precision(True)
+            xs = x[:4].cpu().numpy(); ys = np.empty_like(xs); oh = orc.FftHandler(n, np.float32)
+            cpu = self.cpu_time(lambda: orc.ndfft_par(xs, ys, oh, 1), fl * 4 / b)
+            cpu["sample"] = "4 of 64 rows"
+            orc.set_native_precision(False)
+            del xs, ys
+        med, mn = self.time_call(lambda: nb.ndfft(x, y, h, 1), iters=max(3, self.iters // 3))
+        nbytes = 2 * x.numel() * 8
+        self.add("c5b", "ndfft axis1 64 x 2^24 c64 (four-step)", "f32", med, mn, nbytes, fl, cpu=cpu,
+                 frac_of_two_pass_bound=round(2 * nbytes / (med * 1e-3) / 1e9 / self.peak, 4),
+                 note="frac uses the one-pass byte definition; two HBM passes are unavoidable at this length")
+        del x, y
+
+
+def c2_step_bench(nb, torch, np, dev, local, steps, warmup):
+    """Round 1's headline: ndfft axis 1, ndfft axis 0, ndifft axis 0, ndifft axis 1 on one 8192^2 c64 array per rank."""
+    n = 8192
+    h = nb.FftHandler(n, np.float32, device=local)
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 32 + local)
+    x = torch.complex(torch.rand((n, n), generator=g, device=dev) * 2 - 1, torch.rand((n, n), generator=g, device=dev) * 2 - 1)
+    a = torch.empty_like(x); b = torch.empty_like(x)
+
+    def step():
+        nb.ndfft(x, a, h, 1); nb.ndfft(a, b, h, 0); nb.ndifft(b, a, h, 0); nb.ndifft(a, b, h, 1)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+# per-launch DRAM traffic of the dominant kernel from one `ncu --set full` capture of this command (profiles/)
+C3_TRAFFIC = {"bytes": None, "source": "not captured yet"}
 
 
 def main():
@@ -164,9 +464,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU stand-in legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (c1, c2, c4, c5a, c5b)")
+    ap.add_argument("--only", default="", help="comma list of configs for the table, e.g. c2,c4")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--chunks", type=int, default=int(os.environ.get("NDFB_C3_CHUNKS", "0")), help="i2-chunks of the N>1 exchange pipeline (0 = auto)")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: launch the slab pipeline from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -176,6 +481,7 @@ def main():
     import torch.distributed as dist
 
     import ndrustfft_b200 as nb
+    from ndrustfft_b200.dist import SlabR2cFft3d
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,172 +494,211 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)
-
+    peak, peak_src = measured_peak()
     lib = nb._default_backend().lib
-    h = nb.FftHandler(N_AXIS, np.float32, device=local)
-    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 32 + rank)
-    x = torch.complex(torch.rand((N_AXIS, N_AXIS), generator=g, device=dev) * 2 - 1,
-                      torch.rand((N_AXIS, N_AXIS), generator=g, device=dev) * 2 - 1)
-    a = torch.empty_like(x)
-    b = torch.empty_like(x)
-
-    def step(evs=None):
-        if evs: evs[0].record()
-        nb.ndfft(x, a, h, 1)
-        if evs: evs[1].record()
-        nb.ndfft(a, b, h, 0)
-        if evs: evs[2].record()
-        nb.ndifft(b, a, h, 0)
-        if evs: evs[3].record()
-        nb.ndifft(a, b, h, 1)
-        if evs: evs[4].record()
-
-    for _ in range(W):
-        step()
-    torch.cuda.synchronize()
-    lc0 = lib.launch_count()
-    nb.ndfft(a, b, h, 0)
-    strided_launches = lib.launch_count() - lc0          # kernels one strided-axis call launches
-    nb.ndifft(b, a, h, 0)
-    torch.cuda.synchronize()
-    step()
-    torch.cuda.synchronize()
-    # correctness guard on the bench's own data: the four transforms are a round trip
-    rel = (torch.linalg.vector_norm(b - x) / torch.linalg.vector_norm(x)).item()
-    assert rel < 1e-5, f"round trip rel L2 {rel}"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
-    launches0 = lib.launch_count()
+    def allmax(v):
+        tt = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.item()
+
+    # ---- the headline transform ----
+    chunks = args.chunks or (1 if world == 1 else {2: 1, 4: 2, 8: 4}.get(world, 1))
+    plan = SlabR2cFft3d((N3, N3, N3), np.float64, device=dev, chunks=chunks)
+    s0, s1 = N3 // world, N3 // world
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 48 + rank)
+    x = torch.rand((s0, N3, N3), generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    out = torch.empty((N3, s1, M3), dtype=torch.complex128, device=dev)
+    for _ in range(W):
+        plan.forward(x, out)
+    back = plan.inverse(out)
+    rel = (torch.linalg.vector_norm(back - x) / torch.linalg.vector_norm(x)).item()
+    assert rel < 1e-12, f"round trip rel L2 {rel}"
+    del back
     barrier()
+    lc0 = lib.launch_count()
+    plan.forward(x, out)
+    torch.cuda.synchronize()
+    launches_per_step = lib.launch_count() - lc0
+    use_graph = world > 1 and not args.no_graph
+    run = lambda: plan.forward(x, out)
+    per_replay = 1
+    if use_graph:
+        try:
+            if getattr(plan, "peer", False) and plan._call % 2:
+                plan.forward(x, out)                      # keep the double-buffer parity of capture and replay aligned
+            gr = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(gr, stream=side):
+                    plan.forward(x, out)
+                    plan.forward(x, out)                  # two transforms per replay: both receive buffers
+            torch.cuda.current_stream(dev).wait_stream(side)
+            per_replay = 2
+            run = lambda: gr.replay()
+            run(); torch.cuda.synchronize()
+        except Exception as e:                            # pragma: no cover - depends on the box
+            use_graph = False
+            per_replay = 1
+            run = lambda: plan.forward(x, out)
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture of the slab pipeline failed ({e!r}); host launches", file=sys.stderr)
+    barrier()
+
+    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for k in range(K):
-        step(events[k])
-    t_end.record()
-    barrier()
+    stage_ms = None
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nrep = (K + per_replay - 1) // per_replay
+    if world == 1:
+        # same three launches, with an event between the stages
+        be = plan.be
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+        t_start.record()
+        for k in range(K):
+            evs[k][0].record(); be.ndfft_r2c(x, plan.a, plan.h2, 2)
+            evs[k][1].record(); be.ndfft(plan.a_pad, plan.b_pad, plan.h1, 1)
+            evs[k][2].record(); be.ndfft(plan.b, out, plan.h0, 0)
+            evs[k][3].record()
+        t_end.record()
+        barrier()
+        stage_ms = [sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i in range(3)]
+        steps_done = K
+    else:
+        t_start.record()
+        for _ in range(nrep):
+            run()
+        t_end.record()
+        barrier()
+        steps_done = nrep * per_replay
     clocks = sampler.stop() if rank == 0 else None
-    launches = lib.launch_count() - launches0
-    total_ms = t_start.elapsed_time(t_end)
-    per = [sum(events[k][i].elapsed_time(events[k][i + 1]) for k in range(K)) / K for i in range(4)]
-    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = tmax.item()
-    ms_per_step = total_ms_max / K
-    value = world * 4 * FLOPS_PER_TRANSFORM / (ms_per_step * 1e-3) / 1e9
+    ms_per_step = allmax(t_start.elapsed_time(t_end) / steps_done)
+    value = C3_FLOPS / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: host arrays through the C ABI's NDFB_MEM_HOST path (pinned staging) ----
+    # ---- e2e: pageable host arrays in, pageable host arrays out ----
     e2e = None
     if not args.no_e2e:
-        hx = torch.empty((N_AXIS, N_AXIS), dtype=torch.complex64).pin_memory()
-        ha = torch.empty_like(hx).pin_memory()
-        hb = torch.empty_like(hx).pin_memory()
-        hx.copy_(x)
-        nx, na, nbuf = hx.numpy(), ha.numpy(), hb.numpy()
-
-        call_s = [0.0, 0.0, 0.0, 0.0]
-
-        def host_step():
-            t = [time.perf_counter()]
-            nb.ndfft(nx, na, h, 1); t.append(time.perf_counter())
-            nb.ndfft(na, nbuf, h, 0); t.append(time.perf_counter())
-            nb.ndifft(nbuf, na, h, 0); t.append(time.perf_counter())
-            nb.ndifft(na, nbuf, h, 1); t.append(time.perf_counter())
-            for i in range(4):
-                call_s[i] += t[i + 1] - t[i]
-
-        host_step()
-        barrier()
-        call_s[:] = [0.0, 0.0, 0.0, 0.0]
         KE = max(1, min(args.e2e_steps, K))
-        t0 = time.perf_counter()
-        for _ in range(KE):
-            host_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        et = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        dt = et.item() / KE
-        relh = float(np.linalg.norm(nbuf - nx) / np.linalg.norm(nx))
-        assert relh < 1e-5, relh
-        # the same four transforms as two multi-axis calls (ndfb_exec_chain: fft2 then ifft2): two PCIe round trips, not four
-        def chain_step():
-            nb.fft2(nx, na, h, h)
-            nb.ifft2(na, nbuf, h, h)
+        rng = np.random.default_rng(0xB200 + 48 + rank)
+        if world == 1:
+            hx = rng.uniform(-1, 1, (N3, N3, N3))                      # plain pageable numpy memory
+            hy = np.empty((N3, N3, M3), np.complex128)
+            hr, hc = nb.R2cFftHandler(N3), nb.FftHandler(N3)
+            chain = [("ndfft_r2c", hr, 2), ("ndfft", hc, 1), ("ndfft", hc, 0)]
+            nb.ndchain(hx, hy, chain)
+            t0 = time.perf_counter()
+            for _ in range(KE):
+                nb.ndchain(hx, hy, chain)
+            dt = (time.perf_counter() - t0) / KE
+            # spot check against the device result of the same data
+            xd = torch.from_numpy(hx).to(dev); od = torch.empty((N3, N3, M3), dtype=torch.complex128, device=dev)
+            nb.ndchain(xd, od, chain)
+            relh = (torch.linalg.vector_norm(torch.from_numpy(hy[:8]).to(dev) - od[:8]) / torch.linalg.vector_norm(od[:8])).item()
+            assert relh < 1e-12, relh
+            del xd, od
+            # the same with caller-pinned arrays (an extra: what a caller that registers its memory gets)
+            px = torch.empty((N3, N3, N3), dtype=torch.float64).pin_memory(); py = torch.empty((N3, N3, M3), dtype=torch.complex128).pin_memory()
+            px.copy_(torch.from_numpy(hx))
+            nb.ndchain(px.numpy(), py.numpy(), chain)
+            t0 = time.perf_counter()
+            for _ in range(max(2, KE // 2)):
+                nb.ndchain(px.numpy(), py.numpy(), chain)
+            dtp = (time.perf_counter() - t0) / max(2, KE // 2)
+            del px, py
+            e2e = {"value": C3_FLOPS / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": N3 ** 3 * 8, "d2h_bytes_per_step": N3 * N3 * M3 * 16,
+                   "ms_per_step": dt * 1e3, "steps": KE,
+                   "path": "ndfb_exec_chain(mem=HOST) on PAGEABLE numpy arrays: caller memory -> pinned ring (copy threads) -> H2D | r2c pieces ... axis-0 pieces | D2H -> caller memory",
+                   "pinned_arrays": {"value": C3_FLOPS / dtp / 1e9, "ms_per_step": dtp * 1e3, "note": "same call on caller-pinned arrays (no staging ring)"}}
+            del hx, hy
+        else:
+            hx = rng.uniform(-1, 1, (s0, N3, N3))
+            hy = np.empty((N3, s1, M3), np.complex128)
+            txh, tyh = torch.from_numpy(hx), torch.from_numpy(hy)
 
-        chain_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(KE):
-            chain_step()
-        torch.cuda.synchronize()
-        ct = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
-        cdt_s = ct.item() / KE
-        relc = float(np.linalg.norm(nbuf - nx) / np.linalg.norm(nx))
-        assert relc < 1e-5, relc
-        e2e = {"value": world * 4 * FLOPS_PER_TRANSFORM / dt / 1e9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": 4 * N_AXIS * N_AXIS * 8, "d2h_bytes_per_step": 4 * N_AXIS * N_AXIS * 8,
-               "ms_per_step": dt * 1e3, "steps": KE, "ms_per_call": [round(c / KE * 1e3, 3) for c in call_s],
-               "path": "ndfb_exec(mem=HOST) on pinned numpy arrays, 4 calls/step; each call pipelines H2D | kernel | D2H in pieces",
-               "chained": {"value": world * 4 * FLOPS_PER_TRANSFORM / cdt_s / 1e9, "unit": "GFLOP/s", "ms_per_step": cdt_s * 1e3,
-                           "h2d_bytes_per_step": 2 * N_AXIS * N_AXIS * 8, "d2h_bytes_per_step": 2 * N_AXIS * N_AXIS * 8,
-                           "path": "same four transforms as two ndfb_exec_chain calls (fft2, ifft2): intermediates stay on the GPU"}}
-        del hx, ha, hb
+            def host_step():
+                x.copy_(txh)                       # pageable H2D of this rank's slab
+                plan.forward(x, out)
+                tyh.copy_(out)                     # pageable D2H of this rank's part of the spectrum
+            host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(KE):
+                host_step()
+            torch.cuda.synchronize()
+            dt = allmax(time.perf_counter() - t0) / KE
+            e2e = {"value": C3_FLOPS / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": N3 ** 3 * 8, "d2h_bytes_per_step": N3 * N3 * M3 * 16,
+                   "ms_per_step": dt * 1e3, "steps": KE,
+                   "path": "per rank: pageable numpy slab -> device (torch copy), SlabR2cFft3d.forward, device -> pageable numpy; wall clock, max over ranks"}
+            del hx, hy, txh, tyh
+
+    # ---- c2 weak line (N > 1) ----
+    c2_weak = None
+    if world > 1:
+        ms_c2 = allmax(c2_step_bench(nb, torch, np, dev, local, max(3, K // 2), 3))
+        fl = 4 * 8192 * 5.0 * 8192 * 13
+        c2_weak = {"value": world * fl / (ms_c2 * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_c2, "scaling": "weak",
+                   "workload": "c2 step (4 axis transforms of an 8192^2 c64 array) on an independent array per rank, no collective"}
+
+    # ---- every other BASELINE config, per call (N = 1) ----
+    configs = None
+    if world == 1 and not args.no_configs:
+        del x, out, plan
+        torch.cuda.empty_cache()
+        cb = ConfigBench(nb, torch, np, peak, args.iters, cpu=not args.no_cpu)
+        only = set(args.only.split(",")) if args.only else None
+        for name in ("c1", "c2", "c3", "c4", "c5a", "c5b"):
+            if only is None or name in only:
+                getattr(cb, name)()
+                lib.dll.ndfb_release_workspaces()
+                torch.cuda.empty_cache()
+        configs = cb.rows
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        # The two contiguous-axis calls are ONE launch each of the 8192-point row kernel (2 launches/step, 1 GiB of
-        # algorithmic bytes per launch); each strided-axis call is one persistent launch that runs both column passes
-        # (64- and 128-point) with the intermediate kept in L2.  Shares are in `launches`.
-        rows_ms = 0.5 * (per[0] + per[3])
-        cols_ms = 0.5 * (per[1] + per[2])
-        rows = {"kernel": "sfft_kernel<float, Sched<8192,512,16,16,16,2>, rows> (ndfft/ndifft along the contiguous axis: one launch per call)",
-                "ms": rows_ms, "achieved": BYTES_PER_TRANSFORM / (rows_ms * 1e-3) / 1e9,
-                "frac": BYTES_PER_TRANSFORM / (rows_ms * 1e-3) / 1e9 / peak, "share_of_step": (per[0] + per[3]) / sum(per),
-                "traffic": ROWS_TRAFFIC, "traffic_source": ROWS_TRAFFIC_SRC}
-        cols = {"kernel": ("fs2_kernel<float, Sched<64,...>, 64, Sched<128,...>, 32> (NDFB_FS2=1: both column passes of 8192 = 64 x 128 in one "
-                           "persistent launch, workspace ring in L2)") if strided_launches == 1 else
-                          "two sfft_kernel launches per call: 64-point then 128-point column passes through an HBM workspace (2 x 1 GiB moved)",
-                "launches_per_call": strided_launches, "ms": cols_ms, "achieved": BYTES_PER_TRANSFORM / (cols_ms * 1e-3) / 1e9,
-                "frac": BYTES_PER_TRANSFORM / (cols_ms * 1e-3) / 1e9 / peak, "share_of_step": (per[1] + per[2]) / sum(per),
-                "traffic": COLS_TRAFFIC if strided_launches == 1 else COLS2_TRAFFIC,
-                "traffic_source": COLS_TRAFFIC_SRC if strided_launches == 1 else COLS2_TRAFFIC_SRC}
-        if strided_launches == 2:
-            # each pass kernel moves the whole array once in and once out: its own roofline fraction
-            cols["frac_of_bytes_moved_by_the_two_passes"] = 2 * BYTES_PER_TRANSFORM / (cols_ms * 1e-3) / 1e9 / peak
-        # dominant kernel = the single kernel with the largest share of the step
-        dom, other, other_key = (cols, rows, "contiguous_axis_kernel") if (strided_launches == 1 and cols["share_of_step"] >= rows["share_of_step"]) \
-            else (rows, cols, "strided_axis_call")
         line = {
-            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c2: 8192x8192 c64 ndfft axis1, ndfft axis0, ndifft axis0, ndifft axis1 (one step = 4 axis transforms)",
-                       "l2": "inputs larger than L2 (512 MiB per array, 3 arrays cycled)", "sharding": "independent array per rank, no collective"},
-            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["frac"], "traffic": dom["traffic"], "traffic_source": dom["traffic_source"],
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_TRANSFORM,
-                         "share_of_step": dom["share_of_step"], other_key: other},
-            "launches": [{"name": STEP_NAMES[i], "ms": per[i], "GB/s": BYTES_PER_TRANSFORM / (per[i] * 1e-3) / 1e9,
-                          "frac": BYTES_PER_TRANSFORM / (per[i] * 1e-3) / 1e9 / peak,
-                          "GFLOP/s": FLOPS_PER_TRANSFORM / (per[i] * 1e-3) / 1e9} for i in range(4)],
-            "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
-            "roundtrip_rel_l2": rel, "library": lib.version(),
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps_done, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_of(world),
+            "gpu_launches": launches_per_step * steps_done, "launches_per_step": launches_per_step,
+            "clocks": clocks, "e2e": e2e, "roundtrip_rel_l2": rel, "library": lib.version(),
         }
+        step_bytes = sum(C3_STAGE_BYTES)
+        if world == 1:
+            dom = max(range(3), key=lambda i: stage_ms[i])
+            ach = C3_STAGE_BYTES[dom] / (stage_ms[dom] * 1e-3) / 1e9
+            kernels = ["rsfft_kernel<double, Sched<256,...>, rows, RK_R2C> (r2c of 512-point real rows: 256-point complex core + paired epilogue)",
+                       "sfft_kernel<double, Sched<512,64,8,8,8>, cols> (512-point c128 columns, stride 264 elements)",
+                       "sfft_kernel<double, Sched<512,64,8,8,8>, cols> (512-point c128 columns, stride 512*257 elements)"]
+            line["roofline"] = {"bound": "hbm", "kernel": kernels[dom], "stage": C3_STAGE_NAMES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                                "frac": ach / peak, "traffic": C3_TRAFFIC["bytes"], "traffic_source": C3_TRAFFIC["source"], "peak_source": peak_src,
+                                "algorithmic_bytes_per_launch": C3_STAGE_BYTES[dom], "share_of_step": stage_ms[dom] / sum(stage_ms),
+                                "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                                "stages": [{"name": C3_STAGE_NAMES[i], "ms": stage_ms[i], "GB/s": C3_STAGE_BYTES[i] / (stage_ms[i] * 1e-3) / 1e9,
+                                            "frac": C3_STAGE_BYTES[i] / (stage_ms[i] * 1e-3) / 1e9 / peak,
+                                            "GFLOP/s": C3_STAGE_FLOPS[i] / (stage_ms[i] * 1e-3) / 1e9} for i in range(3)]}
+        else:
+            sent = plan.bytes_sent_per_rank()
+            line["roofline"] = {"bound": "hbm", "achieved": step_bytes / world / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": step_bytes / world / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                "note": "per-GPU algorithmic HBM bytes of the three passes / step time (the step also contains the exchange)",
+                                "nvlink": {"bytes_sent_per_rank": sent, "peak_GBps_per_direction": 770.0, "time_at_peak_ms": sent / 770e9 * 1e3,
+                                           "frac_of_step": sent / 770e9 * 1e3 / ms_per_step,
+                                           "exchange": ("peer stores fused into the axis-1 kernel (ndfb_exec_scatter_out over symmetric memory)"
+                                                        if getattr(plan, "peer", False) else "NCCL all_to_all_single")}}
+            line["pipeline"] = {"chunks": chunks, "cuda_graph": use_graph}
+            line["c2_weak"] = c2_weak
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu:
-            gf, dt, cores, sample = cpu_port_run(2, 1)
-            line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample}
+            gf, dt, cores, sample = cpu_c3_run(2, 1)
+            line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample, "toolchain": cargo_probe()}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -567,3 +567,131 @@ def test_three_pass_split_matches_two_pass(dev):
         assert _rel(y3, x) < 2e-6
     finally:
         del os.environ["NDFB_FS_N1"]
+
+
+# ---- round-2 additions: the holes VERDICT r1 listed ----
+def test_negative_and_reversed_strides_device(dev):
+    """Device views with negative strides (ndarray's slice(s![..;-1]) / invert_axis): base pointer = element [0,...], the
+    kernels walk backwards through memory."""
+    be = dev.be
+    rng = np.random.default_rng(16)
+    base = rng.uniform(-1, 1, (48, 64)) + 1j * rng.uniform(-1, 1, (48, 64))
+    t = torch.from_numpy(base).cuda()
+    x = t.flip(0)            # torch has no negative strides: build the reversed view through the C ABI by hand below
+    import ctypes
+    from ndrustfft_b200 import _lib
+    for axis, n in ((1, 64), (0, 48)):
+        h = be.FftHandler(n)
+        y = torch.zeros((48, 64), dtype=torch.complex128, device="cuda")
+        yv = torch.zeros((48, 64), dtype=torch.complex128, device="cuda")
+        SZ, PD = ctypes.c_size_t * 2, ctypes.c_ssize_t * 2
+        # input: both axes reversed (element [0,0] = last element of the buffer); output: rows reversed
+        in_ptr = t.data_ptr() + (48 * 64 - 1) * 16
+        out_ptr = yv.data_ptr() + (47 * 64) * 16
+        rc = be.lib.dll.ndfb_exec(h._plan, _lib.OP_FFT, _lib.NORM_DEFAULT, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), 2,
+                                  SZ(48, 64), PD(-64, -1), SZ(48, 64), PD(-64, 1), axis, _lib.MEM_DEVICE,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        be.lib.check(rc)
+        want = np.zeros((48, 64), complex)
+        orc.ndfft(np.ascontiguousarray(base[::-1, ::-1]), want, orc.FftHandler(n), axis)
+        got = yv.cpu().numpy()[::-1, :]          # logical output [i, j] lives at physical row 47 - i
+        assert orc.rel_l2(got, want) < 1e-12, axis
+    # real kinds with a reversed transformed axis, strided columns
+    xr = rng.uniform(-1, 1, (128, 40))
+    tr = torch.from_numpy(xr).cuda()
+    yr = torch.zeros((128, 40), dtype=torch.float64, device="cuda")
+    h = be.DctHandler(128)
+    SZ, PD = ctypes.c_size_t * 2, ctypes.c_ssize_t * 2
+    rc = be.lib.dll.ndfb_exec(h._plan, _lib.OP_DCT2, _lib.NORM_DEFAULT, ctypes.c_void_p(tr.data_ptr() + 127 * 40 * 8), ctypes.c_void_p(yr.data_ptr()), 2,
+                              SZ(128, 40), PD(-40, 1), SZ(128, 40), PD(40, 1), 0, _lib.MEM_DEVICE, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    be.lib.check(rc)
+    want = np.zeros((128, 40))
+    orc.nddct2(np.ascontiguousarray(xr[::-1]), want, orc.DctHandler(128), 0)
+    assert orc.rel_l2(yr.cpu().numpy(), want) < 1e-12
+    del x
+
+
+def test_scatter_out_single_gpu(dev):
+    """ndfb_exec_scatter_out on ONE GPU: the block pointers address four regions of one buffer, so the driver's 1-GPU test
+    run covers the store path the multi-GPU slab exchange uses (peer-mapped buffers there)."""
+    be = dev.be
+    rng = np.random.default_rng(17)
+    s0, n1, mp, P = 6, 512, 264, 4
+    s1 = n1 // P
+    x = rng.uniform(-1, 1, (s0, n1, mp)) + 1j * rng.uniform(-1, 1, (s0, n1, mp))
+    xd = torch.from_numpy(x).cuda()
+    recv = torch.zeros((P, s0, s1, mp), dtype=torch.complex128, device="cuda")
+    ptrs = [recv.data_ptr() + p * s0 * s1 * mp * 16 for p in range(P)]
+    be.ndfft_scatter_out(xd, be.FftHandler(n1), 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1), out_block=s1, block_ptrs=ptrs)
+    want = np.fft.fft(x, axis=1)
+    got = recv.cpu().numpy()
+    for p in range(P):
+        assert orc.rel_l2(got[p], want[:, p * s1:(p + 1) * s1, :]) < 1e-12
+    # i2-chunked form (the overlapped pipeline scatters sub-ranges of the last dim)
+    recv.zero_()
+    for lo, hi in ((0, 128), (128, 264)):
+        be.ndfft_scatter_out(xd[:, :, lo:hi], be.FftHandler(n1), 1, out_shape=(s0, n1, hi - lo), out_strides=(s1 * mp, mp, 1), out_block=s1,
+                             block_ptrs=[q + lo * 16 for q in ptrs])
+    got = recv.cpu().numpy()
+    for p in range(P):
+        assert orc.rel_l2(got[p], want[:, p * s1:(p + 1) * s1, :]) < 1e-12
+
+
+def test_pageable_host_arrays_pipelined(host, dev):
+    """Pageable numpy arrays (what ndarray hands the shim) through the pinned staging ring: bit-identical to the device path,
+    for a contiguous-axis call (1-D pieces), a strided-axis call (2-D pieces) and an r2c (shape change)."""
+    be = host.be
+    rng = np.random.default_rng(18)
+    x = (rng.uniform(-1, 1, (4096, 4096)) + 1j * rng.uniform(-1, 1, (4096, 4096))).astype(np.complex64)     # 128 MiB
+    h = be.FftHandler(4096, np.float32)
+    xd = torch.from_numpy(x).cuda()
+    for axis in (1, 0):
+        y = np.zeros_like(x)
+        be.ndfft(x, y, h, axis)
+        yd = torch.empty_like(xd)
+        be.ndfft(xd, yd, h, axis)
+        assert np.array_equal(y, yd.cpu().numpy()), axis
+    xr = rng.uniform(-1, 1, (3000, 4096))
+    yr = np.zeros((3000, 2049), np.complex128)
+    be.ndfft_r2c(xr, yr, be.R2cFftHandler(4096), 1)
+    assert orc.rel_l2(yr, np.fft.rfft(xr, axis=1)) < 1e-12
+    # gappy views of large arrays: packed on the host, pipelined, unpacked; the gaps stay intact
+    big = np.full((2048, 2 * 4096), 1.5 - 0.5j, np.complex64)
+    out = big[:, ::2]
+    be.ndfft(x[:2048], out, h, 1)
+    yd = torch.empty((2048, 4096), dtype=torch.complex64, device="cuda")
+    be.ndfft(xd[:2048], yd, h, 1)
+    assert np.array_equal(np.ascontiguousarray(out), yd.cpu().numpy())
+    assert np.all(big[:, 1::2] == np.complex64(1.5 - 0.5j))
+
+
+def test_config1_in_cuda_graph(dev):
+    """c1 is launch-latency bound: the calls must be capturable into a CUDA graph (plan tables uploaded beforehand)."""
+    be = dev.be
+    rng = np.random.default_rng(19)
+    n = 128
+    x = rng.uniform(-1, 1, (n, n))
+    xd = torch.from_numpy(x).cuda()
+    hr, hc, hd = be.R2cFftHandler(n), be.FftHandler(n), be.DctHandler(n)
+    a = torch.zeros((n, n // 2 + 1), dtype=torch.complex128, device="cuda")
+    b = torch.zeros_like(a)
+    c = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+
+    def calls():
+        be.ndfft_r2c(xd, a, hr, 1); be.ndfft(a, b, hc, 0); be.nddct2(xd, c, hd, 0)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        calls()                                   # warm-up outside the capture: tables, function attributes
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            calls()
+    torch.cuda.current_stream().wait_stream(side)
+    b.zero_(); c.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    want = np.fft.fft(np.fft.rfft(x, axis=1), axis=0)
+    assert orc.rel_l2(b.cpu().numpy(), want) < 1e-12
+    wc = np.zeros((n, n)); orc.nddct2(x, wc, orc.DctHandler(n), 0)
+    assert orc.rel_l2(c.cpu().numpy(), wc) < 1e-12
