@@ -509,37 +509,38 @@ def main():
         return tt.item()
 
     # ---- the headline transform ----
-    chunks = args.chunks or (1 if world == 1 else {2: 1, 4: 2, 8: 4}.get(world, 1))
+    # i2-chunked overlap of the exchange with the last pass loses at every N measured (8 GPUs, CUDA graph: 0.295 ms unchunked,
+    # 0.315 / 0.341 / 0.383 ms with 2 / 4 / 8 chunks; profiles/r2b_c3_probe_n8.jsonl), so the default pipeline is unchunked
+    chunks = args.chunks or 1
     plan = SlabR2cFft3d((N3, N3, N3), np.float64, device=dev, chunks=chunks)
     s0, s1 = N3 // world, N3 // world
     g = torch.Generator(device=dev); g.manual_seed(0xB200 + 48 + rank)
     x = torch.rand((s0, N3, N3), generator=g, device=dev, dtype=torch.float64) * 2 - 1
-    out = torch.empty((N3, s1, M3), dtype=torch.complex128, device=dev)
     for _ in range(W):
-        plan.forward(x, out)
+        out = plan.forward(x)              # result = view of the plan's padded array (aligned tile rows in the last pass)
     back = plan.inverse(out)
     rel = (torch.linalg.vector_norm(back - x) / torch.linalg.vector_norm(x)).item()
     assert rel < 1e-12, f"round trip rel L2 {rel}"
     del back
     barrier()
     lc0 = lib.launch_count()
-    plan.forward(x, out)
+    plan.forward(x)
     torch.cuda.synchronize()
     launches_per_step = lib.launch_count() - lc0
     use_graph = world > 1 and not args.no_graph
-    run = lambda: plan.forward(x, out)
+    run = lambda: plan.forward(x)
     per_replay = 1
     if use_graph:
         try:
             if getattr(plan, "peer", False) and plan._call % 2:
-                plan.forward(x, out)                      # keep the double-buffer parity of capture and replay aligned
+                plan.forward(x)                           # keep the double-buffer parity of capture and replay aligned
             gr = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 with torch.cuda.graph(gr, stream=side):
-                    plan.forward(x, out)
-                    plan.forward(x, out)                  # two transforms per replay: both receive buffers
+                    plan.forward(x)
+                    plan.forward(x)                       # two transforms per replay: both receive buffers
             torch.cuda.current_stream(dev).wait_stream(side)
             per_replay = 2
             run = lambda: gr.replay()
@@ -547,7 +548,7 @@ def main():
         except Exception as e:                            # pragma: no cover - depends on the box
             use_graph = False
             per_replay = 1
-            run = lambda: plan.forward(x, out)
+            run = lambda: plan.forward(x)
             if rank == 0:
                 print(f"[bench] CUDA-graph capture of the slab pipeline failed ({e!r}); host launches", file=sys.stderr)
     barrier()
@@ -566,7 +567,7 @@ def main():
         for k in range(K):
             evs[k][0].record(); be.ndfft_r2c(x, plan.a, plan.h2, 2)
             evs[k][1].record(); be.ndfft(plan.a_pad, plan.b_pad, plan.h1, 1)
-            evs[k][2].record(); be.ndfft(plan.b, out, plan.h0, 0)
+            evs[k][2].record(); be.ndfft(plan.b_pad, plan.out_pad, plan.h0, 0)
             evs[k][3].record()
         t_end.record()
         barrier()
@@ -625,8 +626,8 @@ def main():
 
             def host_step():
                 x.copy_(txh)                       # pageable H2D of this rank's slab
-                plan.forward(x, out)
-                tyh.copy_(out)                     # pageable D2H of this rank's part of the spectrum
+                o = plan.forward(x)
+                tyh.copy_(o)                       # pageable D2H of this rank's part of the spectrum
             host_step()
             barrier()
             t0 = time.perf_counter()
@@ -675,7 +676,7 @@ def main():
             ach = C3_STAGE_BYTES[dom] / (stage_ms[dom] * 1e-3) / 1e9
             kernels = ["rsfft_kernel<double, Sched<256,...>, rows, RK_R2C> (r2c of 512-point real rows: 256-point complex core + paired epilogue)",
                        "sfft_kernel<double, Sched<512,64,8,8,8>, cols> (512-point c128 columns, stride 264 elements)",
-                       "sfft_kernel<double, Sched<512,64,8,8,8>, cols> (512-point c128 columns, stride 512*257 elements)"]
+                       "sfft_kernel<double, Sched<512,64,8,8,8>, cols> (512-point c128 columns, stride 512*264 elements)"]
             line["roofline"] = {"bound": "hbm", "kernel": kernels[dom], "stage": C3_STAGE_NAMES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                                 "frac": ach / peak, "traffic": C3_TRAFFIC["bytes"], "traffic_source": C3_TRAFFIC["source"], "peak_source": peak_src,
                                 "algorithmic_bytes_per_launch": C3_STAGE_BYTES[dom], "share_of_step": stage_ms[dom] / sum(stage_ms),

@@ -89,7 +89,7 @@ NDFB_API size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap)
  * pinned ring slot -> caller memory;  pointers that are already pinned or cudaHostRegister'ed skip the ring.
  * Views with gaps between their elements are packed / unpacked on the host: the library never reads or writes a byte of
  * host memory that is not a logical element of the view (sibling views of one allocation stay intact).
- * Environment: NDFB_HOST_THREADS (copy threads, default min(8, cores/2)), NDFB_STAGE_MB (slot size, default 16).
+ * Environment: NDFB_HOST_THREADS (copy threads, default min(12, 3/4 of the cores)), NDFB_STAGE_MB (slot size, default 16).
  * In place: `in == out` with identical shape and strides is supported for the ops that keep shape and element type
  * (FFT, IFFT, DCT1..4) — every tile is read completely before it is written (the reference always takes a separate
  * output, src/lib.rs:107).  Partially overlapping arrays are not supported. */

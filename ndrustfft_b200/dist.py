@@ -81,6 +81,9 @@ class SlabR2cFft3d:
         self.b_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
         self.a = self.a_pad[:, :, :self.m]
         self.b = self.b_pad[:, :, :self.m]
+        # result storage for forward(x) without an explicit `out`: padded the same way (the caller gets the [:, :, :m] view),
+        # so the last pass reads AND writes aligned 128-byte tile rows (512^3 on one GPU: 0.47 -> 0.36 ms for that pass)
+        self.out_pad = torch.zeros((self.n0, self.s1, self.mp), dtype=self.ct, device=self.device)
         # i2 chunks and their send / receive buffers
         k = max(1, min(int(chunks), self.m)) if P > 1 else 1
         self.chunks = [shard_bounds(self.m, k, c) for c in range(k)]
@@ -127,17 +130,22 @@ class SlabR2cFft3d:
         return self.dist.all_to_all_single(t.view_as_real(recv), t.view_as_real(send), group=self.group, async_op=True)
 
     def forward(self, x, out=None):
-        """x: (n0/P, n1, n2) real -> (n0, n1/P, m) complex."""
+        """x: (n0/P, n1, n2) real -> (n0, n1/P, m) complex.  Without `out` the result is a view of a plan-owned array whose
+        last axis is padded to whole 128-byte lines (fastest); it is overwritten by the next forward()."""
         t, be, P = self.torch, self.be, self.world
         s0, s1, n0, n1 = self.s0, self.s1, self.n0, self.n1
         assert tuple(x.shape) == (s0, n1, self.n2), x.shape
-        if out is None:
-            out = t.empty((n0, s1, self.m), dtype=self.ct, device=self.device)
+        padded_out = out is None
+        if padded_out:
+            out = self.out_pad[:, :, :self.m]                   # a view of the library-owned padded result
         if not (P > 1 and self.peer and len(self.pchunks) == 1 and len(self.rchunks) > 1):
             be.ndfft_r2c(x, self.a, self.h2, 2)
         if P == 1:
             be.ndfft(self.a_pad, self.b_pad, self.h1, 1)        # padded lanes: 264 per row, tiles never straddle rows
-            be.ndfft(self.b, out, self.h0, 0)
+            if padded_out:
+                be.ndfft(self.b_pad, self.out_pad, self.h0, 0)
+            else:
+                be.ndfft(self.b, out, self.h0, 0)
             return out
         if self.peer:
             buf, hdl = self._symm[self._call % 2]
@@ -166,13 +174,19 @@ class SlabR2cFft3d:
                 with t.cuda.stream(self._s2):
                     hdl.barrier()
                 main.wait_stream(self._s2)
-                be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
+                if padded_out:
+                    be.ndfft(recv, self.out_pad, self.h0, 0)
+                else:
+                    be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
                 return out
             if K == 1:
                 be.ndfft_scatter_out(self.a_pad, self.h1, 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1),
                                      out_block=s1, block_ptrs=ptrs)
                 hdl.barrier()                                   # every rank's stores have landed
-                be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
+                if padded_out:
+                    be.ndfft(recv, self.out_pad, self.h0, 0)
+                else:
+                    be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
                 return out
             # pieces of the (padded) spectrum axis: the NVLink-bound scatter of piece c+1 runs on one stream while the
             # HBM-bound axis-0 pass of piece c runs on another
@@ -187,9 +201,12 @@ class SlabR2cFft3d:
                     self._ev[c].record(self._s1)
                 with t.cuda.stream(self._s2):
                     self._s2.wait_event(self._ev[c])
-                    hi_m = min(hi, self.m)
-                    if hi_m > lo:
-                        be.ndfft(recv[:, :, lo:hi_m], out[:, :, lo:hi_m], self.h0, 0)
+                    if padded_out:
+                        be.ndfft(recv[:, :, lo:hi], self.out_pad[:, :, lo:hi], self.h0, 0)
+                    else:
+                        hi_m = min(hi, self.m)
+                        if hi_m > lo:
+                            be.ndfft(recv[:, :, lo:hi_m], out[:, :, lo:hi_m], self.h0, 0)
             main.wait_stream(self._s2)
             return out
         works = []
