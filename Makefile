@@ -18,10 +18,14 @@ EMUOBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/emu/%.o,$(SRCS))
 
 all: $(LIB) $(EMULIB)
 
+# kernel headers embedded as strings for run-time compilation of further schedules (csrc/jit.h)
+$(CSRC)/jit_sources.inc: $(CSRC)/common.h $(CSRC)/butterflies.cuh $(CSRC)/sfft_kernel.cuh tools/embed_src.py
+	python3 tools/embed_src.py
+
 lib: $(LIB)
 emu: $(EMULIB)
 
-$(OBJDIR)/cuda/ndfft_b200.o: $(CSRC)/ndfft_b200.cu $(HDRS)
+$(OBJDIR)/cuda/ndfft_b200.o: $(CSRC)/ndfft_b200.cu $(HDRS) $(CSRC)/jit_sources.inc
 	@mkdir -p $(OBJDIR)/cuda
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
@@ -39,7 +43,7 @@ $(OBJDIR)/emu/%.o: $(CSRC)/%.cu $(KHDRS) tests/emu/simt_emu.h
 
 $(LIB): $(NVOBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared -cudart shared -gencode arch=compute_100a,code=sm_100a -o $@ $(NVOBJS)
+	$(NVCC) -shared -cudart shared -gencode arch=compute_100a,code=sm_100a -o $@ $(NVOBJS) -ldl
 
 $(EMULIB): $(EMUOBJS)
 	$(CXX) -shared -o $@ $(EMUOBJS)

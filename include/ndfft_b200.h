@@ -164,6 +164,14 @@ NDFB_API const char* ndfb_version(void);
  * `gpu_launches`. */
 NDFB_API uint64_t ndfb_launch_count(void);
 
+/* Lengths without an ahead-of-time instantiated schedule get the same register-resident Stockham kernels compiled at
+ * run time for their own radix schedule (NVRTC -> sm_100a cubin, cached in memory and under $NDFB_JIT_CACHE or
+ * ~/.cache/ndfft_b200; rustfft plans any length, src/lib.rs:294-304).  This entry point plans and compiles — without
+ * loading, so it works on a machine without a GPU — the schedule for a `core_n`-point complex core
+ * (rkind < 0: ndfft / ndifft;  0..5: the real kinds R2C, C2R, DCT-I..IV whose core is n/2 or n-1 points) and writes a
+ * JSON description into `info`.  Returns NDFB_E_UNSUPPORTED when the length has no such schedule or libnvrtc is absent. */
+NDFB_API int ndfb_jit_compile_check(int dtype, int rkind, size_t core_n, int cols, char* info, size_t cap);
+
 /* Occupancy hint for the NEXT kernel launch of the calling thread: request at least `bytes` of dynamic shared memory
  * (e.g. 116 KiB => one CTA per SM), so that a link-bound kernel leaves room for another stream's HBM-bound kernel. */
 NDFB_API void ndfb_hint_next_launch_smem(size_t bytes);

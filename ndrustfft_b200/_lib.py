@@ -25,7 +25,7 @@ E_INVALID, E_SIZE_MISMATCH, E_SHAPE, E_AXIS, E_ALLOC, E_CUDA, E_UNSUPPORTED = -1
 
 EXPORTS = (
     "ndfb_plan_create", "ndfb_plan_destroy", "ndfb_plan_describe", "ndfb_exec", "ndfb_exec_scaled", "ndfb_exec_split_out", "ndfb_exec_scatter_out",
-    "ndfb_exec_chain",
+    "ndfb_exec_chain", "ndfb_jit_compile_check",
     "ndfb_hint_next_launch_smem", "ndfb_last_error", "ndfb_version", "ndfb_launch_count", "ndfb_release_workspaces",
 )
 
@@ -75,6 +75,8 @@ class CLib:
         d.ndfb_exec_scatter_out.restype = ci
         d.ndfb_exec_chain.argtypes = [ctypes.POINTER(Step), ci, vp, vp, ci, szp, pdp, szp, pdp, ci, vp]
         d.ndfb_exec_chain.restype = ci
+        d.ndfb_jit_compile_check.argtypes = [ci, ci, cz, ci, ctypes.c_char_p, cz]
+        d.ndfb_jit_compile_check.restype = ci
         d.ndfb_hint_next_launch_smem.argtypes = [cz]
         d.ndfb_hint_next_launch_smem.restype = None
         d.ndfb_last_error.restype = ctypes.c_char_p

@@ -262,6 +262,23 @@ template <> NDFB_HD constexpr double ct_sin<9>(int m) {
     return t[m];
 }
 
+template <> NDFB_HD constexpr double ct_cos<12>(int m) {
+    constexpr double t[12] = {1.0, 0.8660254037844386467637231708, 0.5, 2.067032109826398823649690305e-43, -0.5, -0.8660254037844386467637231708, -1.0, -0.8660254037844386467637231708, -0.5, 2.23387644065498832429194784e-41, 0.5, 0.8660254037844386467637231708};
+    return t[m];
+}
+template <> NDFB_HD constexpr double ct_sin<12>(int m) {
+    constexpr double t[12] = {0.0, 0.5, 0.8660254037844386467637231708, 1.0, 0.8660254037844386467637231708, 0.5, 4.13406421965279764729938061e-43, -0.5, -0.8660254037844386467637231708, -1.0, -0.8660254037844386467637231708, -0.5};
+    return t[m];
+}
+template <> NDFB_HD constexpr double ct_cos<15>(int m) {
+    constexpr double t[15] = {1.0, 0.913545457642600895502127572, 0.6691306063588582138262733307, 0.3090169943749474241022934172, -0.1045284632676534713998341548, -0.5, -0.8090169943749474241022934172, -0.9781476007338056379285667479, -0.9781476007338056379285667479, -0.8090169943749474241022934172, -0.5, -0.1045284632676534713998341548, 0.3090169943749474241022934172, 0.6691306063588582138262733307, 0.913545457642600895502127572};
+    return t[m];
+}
+template <> NDFB_HD constexpr double ct_sin<15>(int m) {
+    constexpr double t[15] = {0.0, 0.4067366430758002077539859903, 0.743144825477394235014697049, 0.9510565162951535721164393334, 0.994521895368273336922691945, 0.8660254037844386467637231708, 0.5877852522924731291687059546, 0.2079116908177593371017422844, -0.2079116908177593371017422844, -0.5877852522924731291687059546, -0.8660254037844386467637231708, -0.994521895368273336922691945, -0.9510565162951535721164393334, -0.743144825477394235014697049, -0.4067366430758002077539859903};
+    return t[m];
+}
+
 template <typename R, int A, int B>
 struct DftCT {
     static NDFB_DEV void run(Cx<R>* v) {
@@ -291,5 +308,9 @@ struct DftCT {
     }
 };
 template <typename R> struct Dft<R, 9> : DftCT<R, 3, 3> {};
+// 12 = 3 x 4, 15 = 3 x 5, 14 = 2 x 7: wider choice of balanced schedules for the run-time compiled lengths (jit.h)
+template <typename R> struct Dft<R, 12> : DftCT<R, 3, 4> {};
+template <typename R> struct Dft<R, 15> : DftCT<R, 3, 5> {};
+template <typename R> struct Dft<R, 14> : DftTwiceOdd<R, 7> {};
 
 }  // namespace ndfb

@@ -1,7 +1,14 @@
 // common.h — types shared by the host plan builder and the device kernels.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation of a schedule (jit.h): NVRTC has no host headers; the kernel sources need only these
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long uintptr_t;
+#else
 #include <cstddef>
 #include <cstdint>
+#endif
 
 #ifdef NDFB_EMU
 #include "simt_emu.h"  // tests/emu: g++-compilable stand-ins for the CUDA spellings (test-only build)
@@ -9,7 +16,9 @@
 #define NDFB_DEV inline
 #define NDFB_DYN_SMEM(name) unsigned char* name = simt::block()->smem
 #else
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #define NDFB_HD __host__ __device__ __forceinline__
 #define NDFB_DEV __device__ __forceinline__
 #define NDFB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]

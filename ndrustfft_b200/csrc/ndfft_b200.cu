@@ -20,6 +20,7 @@
 #include "common.h"
 #include "devapi.h"
 #include "hostio.h"
+#include "jit.h"
 #include "plan.h"
 #include "big_kernels.cuh"
 #include "sfft_inst.h"
@@ -308,6 +309,62 @@ static const SfftEntry* find_sfft(bool f64, int N, bool cols, long long nlanes, 
 template <typename R>
 static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, stream_t stream);
 
+// ---- run-time compiled schedules (csrc/jit.h): every smooth length without an instantiated schedule ----
+#ifndef NDFB_EMU
+static bool jit_enabled() {
+    static const bool off = std::getenv("NDFB_NO_JIT") != nullptr || std::getenv("NDFB_DISABLE_SFFT") != nullptr;
+    return !off;
+}
+static bool jit_warned_once(const char* what) {
+    static std::mutex mu;
+    static std::map<std::string, int> seen;
+    std::lock_guard<std::mutex> g(mu);
+    return seen[what]++ > 0;
+}
+static void jit_set_kind(SfftEntry*, int) {}
+static void jit_set_kind(RsfftEntry* e, int kind) { e->kind = kind; }
+// C2C entry (kind < 0) or real-kind entry; the returned pointers live for the process
+template <class Entry>
+static const Entry* jit_entry(bool f64, int kind, int N, bool cols, long long nlanes) {
+    if (!jit_enabled()) return nullptr;
+    static std::mutex mu;
+    static std::map<std::string, std::unique_ptr<Entry>> reg;
+    JitSched js;
+    if (!jit_plan(N, f64, cols, kind >= 0, nlanes, &js)) return nullptr;
+    char key[160];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    snprintf(key, sizeof key, "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", dev, (int)f64, kind, N, js.TL, js.r[0], js.r[1], js.r[2], js.r[3], js.L, js.cols, js.minb);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = reg.find(key);
+        if (it != reg.end()) return it->second.get();
+    }
+    void* func = nullptr;
+    const int rc = jit_get_kernel(f64, kind, js, &func);
+    if (rc) {
+        if (!jit_warned_once("jit")) fprintf(stderr, "[ndfb] note: run-time schedule compilation unavailable (%s); such lengths use the general kernel\n", err_slot().c_str());
+        err_slot().clear();
+        return nullptr;
+    }
+    std::unique_ptr<Entry> e(new Entry());
+    std::memset((void*)e.get(), 0, sizeof(Entry));
+    e->f64 = f64 ? 1 : 0; e->N = N; e->cols = js.cols; e->L = js.L; e->threads = js.threads; e->E = js.E; e->minb = js.minb; e->fam = 1;
+    for (int i = 0; i < 4; ++i) e->r[i] = js.r[i];
+    e->twtotal = js.twtotal; e->smem = js.smem; e->launch = nullptr; e->jit_func = func;
+    jit_set_kind(e.get(), kind);
+    std::lock_guard<std::mutex> g(mu);
+    auto& slot = reg[key];
+    if (!slot) slot = std::move(e);
+    return slot.get();
+}
+#else
+template <class Entry>
+static const Entry* jit_entry(bool, int, int, bool, long long) { return nullptr; }
+template <typename A>
+static int jit_launch(void*, const A&, unsigned, unsigned, size_t, stream_t) { return fail(NDFB_E_UNSUPPORTED, "no run-time compilation in the emulation build"); }
+#endif
+
 
 template <typename R>
 static int launch_tile(ndfb_plan* p, const LaunchSpec& s, stream_t stream, std::string* describe = nullptr) {
@@ -440,6 +497,7 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     for (int i = 0; i < 8; ++i) a.blk_ptr[i] = s.blk_ptr[i];
     const long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+    if (e->jit_func) return jit_launch(e->jit_func, a, (unsigned)grid, (unsigned)e->threads, e->smem, stream);
     return e->launch(a, (unsigned)grid, stream);
 }
 
@@ -472,9 +530,10 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
                           (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
         const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>), s.max_L);
         if (!e && s.max_L) e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
+        if (!e && nlanes > 0) e = jit_entry<SfftEntry>(sizeof(R) == 8, -1, t.N, cols, nlanes);
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
-            if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A');
+            if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c%s radix=%d.%d.%d.%d\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A', e->jit_func ? " jit" : "", e->r[0], e->r[1], e->r[2], e->r[3]);
             return launch_sfft<R>(p, e, s, stream);
         }
     }
@@ -586,9 +645,12 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             }
         }
         const RsfftEntry* e = ok ? find_rsfft(sizeof(R) == 8, rk, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(R)) : nullptr;
+        if (!e && ok && nlanes > 0) {
+            e = jit_entry<RsfftEntry>(sizeof(R) == 8, rk, t.N, cols, nlanes);
+        }
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
-            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A');
+            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c%s\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A', e->jit_func ? " jit" : "");
             RsfftArgs a;
             std::memset(&a, 0, sizeof a);
             a.in = s.in; a.out = s.out; a.nlanes = nlanes;
@@ -608,6 +670,7 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             a.tw = twd;
             const long long grid = (nlanes + e->L - 1) / e->L;
             if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+            if (e->jit_func) return jit_launch(e->jit_func, a, (unsigned)grid, (unsigned)e->threads, e->smem, stream);
             return e->launch(a, (unsigned)grid, stream);
         }
     }
@@ -1163,6 +1226,12 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
             const SfftEntry* e = find_sfft(sizeof(R) == 8, (int)p->n, true, nl);
             const char* ov = std::getenv("NDFB_STRIDED_FOURSTEP");
             bool narrow = e ? (size_t)e->L * cs < 32 : true;
+#ifndef NDFB_EMU
+            if (!e && jit_enabled()) {   // a run-time compiled single-pass schedule with a wide enough tile beats two passes
+                JitSched js;
+                if (jit_plan((int)p->n, sizeof(R) == 8, true, false, nl, &js)) narrow = (size_t)js.L * cs < 32;
+            }
+#endif
             if (ov) narrow = ov[0] == '1';
             if (narrow) single = false;
         }
@@ -1767,6 +1836,28 @@ size_t ndfb_plan_describe(const ndfb_plan* plan, char* buf, size_t cap) {
         buf[ncopy] = 0;
     }
     return s.size() + 1;
+}
+
+int ndfb_jit_compile_check(int dtype, int rkind, size_t core_n, int cols, char* info, size_t cap) {
+#ifdef NDFB_EMU
+    (void)dtype; (void)rkind; (void)core_n; (void)cols; (void)info; (void)cap;
+    return fail(NDFB_E_UNSUPPORTED, "no run-time compilation in the emulation build");
+#else
+    JitSched js;
+    if (core_n > (size_t)(1 << 20) || !jit_plan((int)core_n, dtype == NDFB_F64, cols != 0, rkind >= 0, 1 << 20, &js))
+        return fail(NDFB_E_UNSUPPORTED, "no run-time schedule for a %zu-point core (not 13-smooth, more than 4 passes, or too long for one CTA)", core_n);
+    char expr[256];
+    const char* R = dtype == NDFB_F64 ? "double" : "float";
+    if (rkind < 0)
+        snprintf(expr, sizeof expr, "ndfb::sfft_kernel<%s, ndfb::Sched<%d, %d, %d, %d, %d, %d>, %d, %s, %d>", R, js.N, js.TL, js.r[0], js.r[1], js.r[2], js.r[3], js.L, js.cols ? "true" : "false", js.minb);
+    else
+        snprintf(expr, sizeof expr, "ndfb::rsfft_kernel<%s, ndfb::Sched<%d, %d, %d, %d, %d, %d>, %d, %s, %d, %d>", R, js.N, js.TL, js.r[0], js.r[1], js.r[2], js.r[3], js.L, js.cols ? "true" : "false", rkind, js.minb);
+    std::vector<char> cubin;
+    std::string lowered, log;
+    const int rc = jit_compile(expr, &cubin, &lowered, &log);
+    if (info && cap) snprintf(info, cap, "{\"kernel\":\"%s\",\"threads\":%d,\"smem\":%zu,\"E\":%d,\"cubin_bytes\":%zu}", expr, js.threads, js.smem, js.E, cubin.size());
+    return rc;
+#endif
 }
 
 void ndfb_hint_next_launch_smem(size_t bytes) { launch_smem_floor() = bytes; }

@@ -695,3 +695,40 @@ def test_config1_in_cuda_graph(dev):
     assert orc.rel_l2(b.cpu().numpy(), want) < 1e-12
     wc = np.zeros((n, n)); orc.nddct2(x, wc, orc.DctHandler(n), 0)
     assert orc.rel_l2(c.cpu().numpy(), wc) < 1e-12
+
+
+# ---- run-time compiled schedules (csrc/jit.h): smooth lengths without an ahead-of-time instance ----
+@pytest.mark.parametrize("n", [96, 192, 720, 768, 1200, 1536, 3072, 6561, 1001])
+def test_jit_lengths_c2c(dev, n, capfd):
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        dev.run("ndfft", n, (6, n), 1, np.float64, seed=n)
+        dev.run("ndifft", n, (n, 12), 0, np.float32, seed=n + 1)
+        dev.run("ndfft", n, (3, n, 5), 1, np.float64, seed=n + 2, norm="none")
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    if "run-time schedule compilation unavailable" in err:
+        pytest.skip("libnvrtc not usable on this box")
+    # sfft_kernel instances compiled at run time, not the general tile kernel (6561-point columns do not fit one CTA four
+    # lanes wide: they run as 81 x 81 two-pass transforms on instantiated schedules)
+    assert err.count(" jit ") >= (1 if n == 6561 else 3), err
+    assert "tile_kernel" not in err
+
+
+@pytest.mark.parametrize("op", ["ndfft_r2c", "ndifft_r2c", "nddct1", "nddct2", "nddct3", "nddct4"])
+@pytest.mark.parametrize("n", [96, 720, 1536])
+def test_jit_lengths_real_kinds(dev, op, n, capfd):
+    import os
+    nn = n + 1 if op == "nddct1" else n
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        dev.run(op, nn, (5, nn), 1, np.float64, seed=n)
+        dev.run(op, nn, (nn, 9), 0, np.float32, seed=n + 1)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    if "run-time schedule compilation unavailable" in err:
+        pytest.skip("libnvrtc not usable on this box")
+    assert err.count("[ndfb] rsfft") == 2 and err.count(" jit") >= 2, err
