@@ -574,6 +574,8 @@ def main():
         stage_ms = [sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i in range(3)]
         steps_done = K
     else:
+        if getattr(plan, "peer", False):
+            plan._symm[0][1].barrier()             # device-side rendezvous: every GPU enters the timed region within microseconds
         t_start.record()
         for _ in range(nrep):
             run()

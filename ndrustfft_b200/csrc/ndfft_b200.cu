@@ -495,6 +495,16 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     a.os_blk = s.os_blk; a.os_blk_stride = s.os_blk_stride;
     a.nblk_ptr = s.nblk_ptr;
     for (int i = 0; i < 8; ++i) a.blk_ptr[i] = s.blk_ptr[i];
+    // Scattered blocks that are contiguous per (tile, destination) go out as bulk-async copies (sfft_body MODE 3): column tile
+    // over the fastest batch dim, that dim contiguous in the output and a whole number of tiles long, rows of a block L apart.
+    if (s.nblk_ptr && e->cols && e->r[1] > 1 && e->N >= 64 && e->N <= 2048 && !s.fs_twiddle && !s.dims.empty() && s.dims[0].os == 1 && s.dims[0].size % e->L == 0 &&
+        s.os_axis == e->L && (size_t)s.os_blk * e->L * sizeof(Cx<R>) % 16 == 0 && !std::getenv("NDFB_NO_BULK_STORE")) {
+        bool aligned = true;
+        for (int i = 0; i < s.nblk_ptr; ++i) if ((uintptr_t)s.blk_ptr[i] % 16) aligned = false;
+        for (size_t d = 1; d < s.dims.size(); ++d) if ((s.dims[d].os * (long long)sizeof(Cx<R>)) % 16) aligned = false;
+        a.bulk_store = aligned ? 1 : 0;
+    }
+    if (a.bulk_store && std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] scatter blocks as bulk-async copies: %d x %zu bytes per tile\n", s.nblk_ptr, (size_t)s.os_blk * e->L * sizeof(Cx<R>));
     const long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
     if (e->jit_func) return jit_launch(e->jit_func, a, (unsigned)grid, (unsigned)e->threads, e->smem, stream);

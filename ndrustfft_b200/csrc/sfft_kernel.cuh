@@ -36,6 +36,8 @@ struct SfftArgs {
     long long os_blk_stride;  // ... with this stride for the block index (packed all-to-all send layout)
     int nblk_ptr;          // != 0: block p is written relative to blk_ptr[p] (peer-mapped receive buffers: the store IS the all-to-all)
     void* blk_ptr[8];
+    int bulk_store;        // != 0 (with nblk_ptr): the tile's block for each destination is one contiguous range there: stage the result
+                           // in shared memory and send each block with ONE bulk-async copy (cp.async.bulk, the TMA engine)
     const void* fs_lo;
     const void* fs_hi;
 };
@@ -277,6 +279,31 @@ NDFB_DEV LaneBase lane_base(const A& a, long long g, bool valid, int fs_dim = 0)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// bulk-async (TMA) stores: shared memory -> global / peer memory, one instruction per contiguous block
+// ------------------------------------------------------------------------------------------------------
+#ifdef NDFB_EMU
+NDFB_DEV void bulk_store_fence() {}
+NDFB_DEV void bulk_store_issue(void* gdst, const void* ssrc, unsigned bytes) {
+    unsigned char* d = reinterpret_cast<unsigned char*>(gdst);
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(ssrc);
+    for (unsigned i = 0; i < bytes; ++i) d[i] = q[i];
+}
+NDFB_DEV void bulk_store_commit_and_drain() {}
+#else
+// generic-proxy writes (the STS of the last pass) must be visible to the async proxy before it reads shared memory
+NDFB_DEV void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+NDFB_DEV void bulk_store_issue(void* gdst, const void* ssrc, unsigned bytes) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+// the CTA may not exit (or reuse the buffer) before the engine has READ the staged tile
+NDFB_DEV void bulk_store_commit_and_drain() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------------
 // complex-to-complex
 // ------------------------------------------------------------------------------------------------------
 // MODE 0: plain store;  1: four-step twiddle from the single table W_N^e (N <= 2^17), nothing else;  2: everything
@@ -293,7 +320,7 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     const bool valid = c.valid;
     const int j2 = lb.j2;
     Cx<R> v[S::E];
-    if constexpr (MODE != 2) {
+    if constexpr (MODE == 0 || MODE == 1) {
         SfftGLoad<R, CG> gl; gl.in = in; gl.is_axis = is_axis; gl.sgn = sgn_in; gl.valid = valid;
         SfftGStore<R, MODE> gs; gs.out = out; gs.os_axis = os_axis; gs.sc = sc; gs.sy = sy; gs.valid = valid;
         gs.fs = reinterpret_cast<const Cx<R>*>(a.fs_lo); gs.j2 = (unsigned)j2;
@@ -306,6 +333,25 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
         x.y *= sgn_in;
         return x;
     };
+    if constexpr (MODE == 3) {
+        // Scattered output blocks whose per-destination part of this tile is contiguous (blocked exchange layout, column
+        // tiles): the last pass stores the tile in natural order [k][lane] into the shared buffer, then ONE bulk-async copy
+        // per destination moves os_blk * L elements straight into that GPU's memory.  The store IS the all-to-all, issued by
+        // the TMA engine in large transactions instead of 16-byte st.global per thread.
+        static_assert(COLS, "bulk block stores are for column tiles");
+        auto stage = [&](int k, Cx<R> val) { c.smem[k * L + c.l] = cmake<R>(val.x * sc, val.y * sy); };
+        SfftAll<R, S, L, COLS, 0, false, (S::NP > 1)>::run(c, v, tw, load, stage);
+        bulk_store_fence();                         // every writer: its stores become visible to the async proxy ...
+        __syncthreads();                            // ... and the issuing threads are ordered after all of them
+        if (threadIdx.x < (unsigned)a.nblk_ptr) {   // thread p sends block p (only lane 0's base is used)
+            const LaneBase lb0 = lane_base(a, (long long)blockIdx.x * L, true, 0);
+            const int p = (int)threadIdx.x;
+            bulk_store_issue(reinterpret_cast<Cx<R>*>(a.blk_ptr[p]) + lb0.bo, c.smem + (size_t)p * a.os_blk * L,
+                             (unsigned)(sizeof(Cx<R>) * (size_t)a.os_blk * L));
+            bulk_store_commit_and_drain();
+        }
+        return;
+    }
     auto store = [&](int k, Cx<R> val) {
         if (!valid) return;
         Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
@@ -331,6 +377,11 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
 }
 
+// lengths whose column kernels carry the bulk-async scatter epilogue (the axis lengths a slab exchange splits; keeping the
+// variant out of the other ~400 column instances keeps the library and its build time down)
+template <class S, bool COLS>
+constexpr bool kSfftBulkStore = COLS && S::NP > 1 && S::N >= 64 && S::N <= 2048;
+
 template <typename R, class S, int L, bool COLS, int MINB>
 __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_constant__ SfftArgs a) {
     NDFB_DYN_SMEM(smem_raw);
@@ -346,7 +397,9 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, 0, true>(a, c, lb);
     else if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb);
     else if (a.fs_twiddle && a.fs_shift >= 40 && !a.os_blk) sfft_body<R, S, L, COLS, 1, false>(a, c, lb);
-    else sfft_body<R, S, L, COLS, 2, false>(a, c, lb);
+    else if (kSfftBulkStore<S, COLS> && a.bulk_store) {
+        if constexpr (kSfftBulkStore<S, COLS>) sfft_body<R, S, L, COLS, 3, false>(a, c, lb);
+    } else sfft_body<R, S, L, COLS, 2, false>(a, c, lb);
 }
 
 // ------------------------------------------------------------------------------------------------------

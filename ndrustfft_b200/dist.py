@@ -51,7 +51,7 @@ class SlabR2cFft3d:
     """
 
     def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto",
-                 row_chunks=1, scatter_smem=None):
+                 row_chunks=1, scatter_smem=None, blocked=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -76,6 +76,8 @@ class SlabR2cFft3d:
         # internal work arrays keep the spectrum axis padded to a multiple of 128 bytes (257 -> 264 complex f64) so that
         # every L-lane tile row of the strided passes - and every peer store - is one aligned 128-byte line
         lanes128 = 128 // (8 if self.rdt == np.float32 else 16)
+        self.lanes128 = lanes128
+        self.blocked = bool(blocked)
         self.mp = -(-self.m // lanes128) * lanes128
         self.a_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
         self.b_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
@@ -179,6 +181,18 @@ class SlabR2cFft3d:
                 else:
                     be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
                 return out
+            if K == 1 and self.blocked and padded_out:
+                # Blocked receive layout [i0][i2 block][j1][lane]: what one tile of the axis-1 kernel sends to one destination
+                # (64 rows x 128 bytes at 8 GPUs) is ONE contiguous 8 KiB block of that GPU's memory instead of 64 rows 4 KiB
+                # apart, so consecutive warp stores are address-adjacent on the NVLink side.  Only the stride description
+                # changes: the same kernels run (batch dims lane / j1 / i2-block with different in and out strides).
+                lb = self.lanes128
+                nb_ = mp // lb
+                be.ndfft_scatter_out(self.a_pad.view(s0, n1, nb_, lb), self.h1, 1, out_shape=(s0, n1, nb_, lb),
+                                     out_strides=(s1 * mp, lb, s1 * lb, 1), out_block=s1, block_ptrs=ptrs)
+                hdl.barrier()
+                be.ndfft(buf.view(n0, nb_, s1, lb).permute(0, 2, 1, 3), self.out_pad.view(n0, s1, nb_, lb), self.h0, 0)
+                return out
             if K == 1:
                 be.ndfft_scatter_out(self.a_pad, self.h1, 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1),
                                      out_block=s1, block_ptrs=ptrs)
@@ -233,6 +247,24 @@ class SlabR2cFft3d:
         if P == 1:
             be.ndifft(X, self.b, self.h0, 0)
             be.ndifft(self.b, self.a, self.h1, 1)
+            be.ndifft_r2c(self.a, out, self.h2, 2)
+            return out
+        if self.peer:
+            # The inverse exchange through peer memory as well (examples/rfft2.rs:49-53 order: last axis' inverse first):
+            # the axis-0 inverse pass stores plane i0 straight into the GPU that owns it, at columns rank*s1.. of that
+            # GPU's (s0, n1, mp) array — no NCCL call, no permute copy.
+            buf, hdl = self._symm[self._call % 2]
+            self._call += 1
+            esz = 8 if self.rdt == np.float32 else 16
+            mp = self.mp
+            ptrs = [int(hdl.buffer_ptrs[p]) + self.rank * s1 * mp * esz for p in range(P)]
+            padded_in = X.data_ptr() == self.out_pad.data_ptr() and tuple(X.stride()) == (s1 * mp, mp, 1)
+            src, width = (self.out_pad, mp) if padded_in else (X, self.m)
+            be.ndfft_scatter_out(src, self.h0, 0, out_shape=(n0, s1, width), out_strides=(n1 * mp, mp, 1), out_block=s0,
+                                 block_ptrs=ptrs, inverse=True)
+            hdl.barrier()
+            recv = buf.view(s0, n1, mp)
+            be.ndifft(recv, self.a_pad, self.h1, 1)
             be.ndifft_r2c(self.a, out, self.h2, 2)
             return out
         works = []

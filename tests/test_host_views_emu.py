@@ -160,3 +160,52 @@ def test_python_mirror_rejects_bad_arrays(be):
     yc = buf.view(complex)[:2 * (n // 2 + 1)].reshape(2, n // 2 + 1)
     with pytest.raises(ValueError, match="overlap"):
         be.ndfft_r2c(xr, yc, hr, 1)
+
+
+def test_blocked_exchange_layout_is_a_stride_description(be):
+    """dist.SlabR2cFft3d's blocked receive layout [i0][i2 block][j1][lane]: the scatter store and the last pass only see
+    different strides.  Checked here on one process: 'peers' are regions of one buffer."""
+    rng = np.random.default_rng(6)
+    s0, n1, lb, nb, P = 2, 64, 8, 3, 4
+    mp, s1 = lb * nb, n1 // P
+    n0 = s0 * P
+    a = _cx(rng, (s0, n1, mp))
+    # every 'rank' sends the same local array; rank r's planes land in chunk r of each destination buffer
+    bufs = [np.zeros(P * s0 * s1 * mp, complex) for _ in range(P)]
+    h1, h0 = be.FftHandler(n1), be.FftHandler(n0)
+    chunk = s0 * s1 * mp * 16
+    for r in range(P):
+        be.ndfft_scatter_out(a.reshape(s0, n1, nb, lb), h1, 1, out_shape=(s0, n1, nb, lb), out_strides=(s1 * mp, lb, s1 * lb, 1),
+                             out_block=s1, block_ptrs=[b.ctypes.data + r * chunk for b in bufs])
+    fa = np.fft.fft(a, axis=1)
+    for d in range(P):
+        recv = bufs[d].reshape(n0, nb, s1, lb).transpose(0, 2, 1, 3)           # logical (i0, j1, i2 block, lane)
+        want = np.concatenate([fa[:, d * s1:(d + 1) * s1, :]] * P, axis=0).reshape(n0, s1, nb, lb)
+        assert orc.rel_l2(recv, want) < 1e-12
+        out = np.zeros((n0, s1, mp), complex)
+        be.ndfft(recv, out.reshape(n0, s1, nb, lb), h0, 0)
+        assert orc.rel_l2(out, np.fft.fft(want.reshape(n0, s1, mp), axis=0)) < 1e-12
+
+
+def test_bulk_async_scatter_blocks(be, capfd):
+    """512-point c128 columns, tile 8 lanes wide, blocked layout: each (tile, destination) block is contiguous, so the kernel
+    stages the tile and sends every block with one bulk copy (cp.async.bulk on the GPU; a byte loop under the emulator)."""
+    rng = np.random.default_rng(7)
+    s0, n1, lb, nb, P = 1, 512, 8, 2, 4
+    mp, s1 = lb * nb, n1 // P
+    a = _cx(rng, (s0, n1, mp))
+    bufs = [np.zeros(s0 * s1 * mp, complex) for _ in range(P)]
+    with _env(NDFB_TRACE=1):
+        be.ndfft_scatter_out(a.reshape(s0, n1, nb, lb), be.FftHandler(n1), 1, out_shape=(s0, n1, nb, lb), out_strides=(s1 * mp, lb, s1 * lb, 1),
+                             out_block=s1, block_ptrs=[b.ctypes.data for b in bufs])
+    assert "bulk-async copies: 4 x 16384 bytes" in capfd.readouterr().err
+    fa = np.fft.fft(a, axis=1)
+    for d in range(P):
+        got = bufs[d].reshape(s0, nb, s1, lb).transpose(0, 2, 1, 3).reshape(s0, s1, mp)
+        assert orc.rel_l2(got, fa[:, d * s1:(d + 1) * s1, :]) < 1e-12
+    with _env(NDFB_NO_BULK_STORE=1):
+        b2 = [np.zeros(s0 * s1 * mp, complex) for _ in range(P)]
+        be.ndfft_scatter_out(a.reshape(s0, n1, nb, lb), be.FftHandler(n1), 1, out_shape=(s0, n1, nb, lb), out_strides=(s1 * mp, lb, s1 * lb, 1),
+                             out_block=s1, block_ptrs=[b.ctypes.data for b in b2])
+    for d in range(P):
+        assert np.array_equal(b2[d], bufs[d])

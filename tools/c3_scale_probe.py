@@ -12,6 +12,7 @@ ap.add_argument("--chunks", default="1,2,4,8")
 ap.add_argument("--graph", default="0,1")
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--phases", type=int, default=1)
+ap.add_argument("--blocked", default="1,0")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -64,6 +65,9 @@ if a.phases and world > 1:
     ph["r2c_ms"] = timed(lambda: be.ndfft_r2c(x, plan.a, plan.h2, 2), 10)
     ph["axis1_local_ms"] = timed(lambda: be.ndfft(plan.a_pad, plan.b_pad, plan.h1, 1), 10)
     ph["axis1_scatter_ms"] = timed(lambda: be.ndfft_scatter_out(plan.a_pad, plan.h1, 1, out_shape=(s0, n, mp), out_strides=(s1 * mp, mp, 1), out_block=s1, block_ptrs=ptrs), 10)
+    lb_ = plan.lanes128; nb_ = mp // lb_
+    ph["axis1_scatter_blocked_ms"] = timed(lambda: be.ndfft_scatter_out(plan.a_pad.view(s0, n, nb_, lb_), plan.h1, 1, out_shape=(s0, n, nb_, lb_), out_strides=(s1 * mp, lb_, s1 * lb_, 1), out_block=s1, block_ptrs=ptrs), 10)
+    ph["axis0_blocked_ms"] = timed(lambda: be.ndfft(buf.view(n, nb_, s1, lb_).permute(0, 2, 1, 3), plan.out_pad.view(n, s1, nb_, lb_), plan.h0, 0), 10)
     ph["barrier_ms"] = timed(lambda: hdl.barrier(), 10)
     ph["axis0_ms"] = timed(lambda: be.ndfft(recv, plan.out_pad, plan.h0, 0), 10)
     sent = plan.bytes_sent_per_rank()
@@ -72,10 +76,10 @@ if a.phases and world > 1:
     emit(ph)
     del plan
 
-for chunks in [int(v) for v in a.chunks.split(",")]:
-    if world == 1 and chunks > 1:
+for chunks, blocked in [(int(v), int(b)) for v in a.chunks.split(",") for b in a.blocked.split(",")]:
+    if (world == 1 and chunks > 1) or (chunks > 1 and blocked):
         continue
-    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=chunks)
+    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=chunks, blocked=bool(blocked))
     for _ in range(3):
         out = plan.forward(x)
     back = plan.inverse(out)
@@ -99,7 +103,7 @@ for chunks in [int(v) for v in a.chunks.split(",")]:
                 emit({"chunks": chunks, "graph": 1, "error": repr(e)[:300]})
                 continue
         ms = timed(run, a.steps, per)
-        emit({"cfg": "c3", "n_gpus": world, "chunks": chunks, "cuda_graph": bool(graph), "ms": ms, "GFLOP/s": FLOPS / (ms * 1e-3) / 1e9,
+        emit({"cfg": "c3", "n_gpus": world, "chunks": chunks, "blocked": bool(blocked), "cuda_graph": bool(graph), "ms": ms, "GFLOP/s": FLOPS / (ms * 1e-3) / 1e9,
               "peer": bool(getattr(plan, "peer", False)), "roundtrip_rel_l2": rel,
               "nvlink_ms_at_770": plan.bytes_sent_per_rank() / 770e9 * 1e3 if world > 1 else 0.0})
     del plan
