@@ -157,6 +157,19 @@ NDFB_API int ndfb_exec_chain(const ndfb_step* steps, int nsteps,
                     const size_t* shape_out, const ptrdiff_t* strides_out,
                     int mem, void* stream);
 
+/* Device memory and streams for hosts without CUDA bindings of their own (the Rust shim's `DeviceArray` / `Stream`,
+ * SURVEY.md 8f-2): arrays allocated here are passed to ndfb_exec / ndfb_exec_chain with mem = NDFB_MEM_DEVICE, so a chain
+ * of transforms pays PCIe once on the way in and once on the way out instead of on every axis (the reference's callers
+ * compose axes through `work` arrays, examples/fft2.rs:23-27).  ndfb_memcpy is asynchronous on `stream` for H2D / D2D
+ * (pageable host memory goes through the pinned ring) and returns after completion for D2H. */
+enum ndfb_copy_kind { NDFB_COPY_H2D = 0, NDFB_COPY_D2H = 1, NDFB_COPY_D2D = 2 };
+NDFB_API int ndfb_device_alloc(void** ptr, size_t bytes, int device);
+NDFB_API void ndfb_device_free(void* ptr);
+NDFB_API int ndfb_memcpy(void* dst, const void* src, size_t bytes, int kind, int device, void* stream);
+NDFB_API int ndfb_stream_create(void** stream, int device);
+NDFB_API void ndfb_stream_destroy(void* stream);
+NDFB_API int ndfb_stream_sync(void* stream);
+
 /* Library identification: "ndfft_b200 <version> sm_100a" for the CUDA build. */
 NDFB_API const char* ndfb_version(void);
 

@@ -26,6 +26,7 @@ E_INVALID, E_SIZE_MISMATCH, E_SHAPE, E_AXIS, E_ALLOC, E_CUDA, E_UNSUPPORTED = -1
 EXPORTS = (
     "ndfb_plan_create", "ndfb_plan_destroy", "ndfb_plan_describe", "ndfb_exec", "ndfb_exec_scaled", "ndfb_exec_split_out", "ndfb_exec_scatter_out",
     "ndfb_exec_chain", "ndfb_jit_compile_check",
+    "ndfb_device_alloc", "ndfb_device_free", "ndfb_memcpy", "ndfb_stream_create", "ndfb_stream_destroy", "ndfb_stream_sync",
     "ndfb_hint_next_launch_smem", "ndfb_last_error", "ndfb_version", "ndfb_launch_count", "ndfb_release_workspaces",
 )
 
@@ -77,6 +78,18 @@ class CLib:
         d.ndfb_exec_chain.restype = ci
         d.ndfb_jit_compile_check.argtypes = [ci, ci, cz, ci, ctypes.c_char_p, cz]
         d.ndfb_jit_compile_check.restype = ci
+        d.ndfb_device_alloc.argtypes = [ctypes.POINTER(vp), cz, ci]
+        d.ndfb_device_alloc.restype = ci
+        d.ndfb_device_free.argtypes = [vp]
+        d.ndfb_device_free.restype = None
+        d.ndfb_memcpy.argtypes = [vp, vp, cz, ci, ci, vp]
+        d.ndfb_memcpy.restype = ci
+        d.ndfb_stream_create.argtypes = [ctypes.POINTER(vp), ci]
+        d.ndfb_stream_create.restype = ci
+        d.ndfb_stream_destroy.argtypes = [vp]
+        d.ndfb_stream_destroy.restype = None
+        d.ndfb_stream_sync.argtypes = [vp]
+        d.ndfb_stream_sync.restype = ci
         d.ndfb_hint_next_launch_smem.argtypes = [cz]
         d.ndfb_hint_next_launch_smem.restype = None
         d.ndfb_last_error.restype = ctypes.c_char_p

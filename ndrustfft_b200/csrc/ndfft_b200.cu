@@ -1870,6 +1870,68 @@ int ndfb_jit_compile_check(int dtype, int rkind, size_t core_n, int cols, char* 
 #endif
 }
 
+// ---- device memory / stream helpers for hosts without CUDA bindings (the Rust shim's DeviceArray and Stream) ----
+int ndfb_device_alloc(void** ptr, size_t bytes, int device) {
+    if (!ptr) return fail(NDFB_E_INVALID, "null pointer");
+    DeviceGuard guard; (void)guard;
+    int rc = dev_set(device);
+    if (rc) return rc;
+    return dev_malloc(ptr, bytes);
+}
+void ndfb_device_free(void* ptr) { if (ptr) dev_free(ptr); }
+int ndfb_memcpy(void* dst, const void* src, size_t bytes, int kind, int device, void* stream) {
+    if ((!dst || !src) && bytes) return fail(NDFB_E_INVALID, "null pointer");
+    if (kind != NDFB_COPY_H2D && kind != NDFB_COPY_D2H && kind != NDFB_COPY_D2D) return fail(NDFB_E_INVALID, "unknown copy kind %d", kind);
+    if (bytes == 0) return 0;
+#ifdef NDFB_EMU
+    (void)device; (void)stream;
+    std::memcpy(dst, src, bytes);
+    return 0;
+#else
+    DeviceGuard guard; (void)guard;
+    int rc = dev_set(device);
+    if (rc) return rc;
+    const cudaMemcpyKind k = kind == NDFB_COPY_H2D ? cudaMemcpyHostToDevice : kind == NDFB_COPY_D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    // pageable host memory moves through the calling thread's pinned ring in slot-sized pieces (hostio.h)
+    if (kind != NDFB_COPY_D2D && bytes >= ((size_t)4 << 20)) {
+        const void* host = kind == NDFB_COPY_H2D ? src : dst;
+        if (host_ptr_pageable(host)) {
+            if ((rc = g_pipe.init(device))) return rc;
+            StageRing& ring = g_pipe.ring;
+            cudaStream_t s = (cudaStream_t)stream;
+            if (kind == NDFB_COPY_H2D) rc = ring.h2d(dst, bytes, src, bytes, bytes, 1, true, s);
+            else { rc = ring.d2h(dst, bytes, src, bytes, bytes, 1, true, s); if (!rc) rc = ring.drain(true); }
+            return rc;
+        }
+    }
+    NDFB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+    if (kind == NDFB_COPY_D2H) NDFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // the host may read `dst` on return
+    return 0;
+#endif
+}
+int ndfb_stream_create(void** stream, int device) {
+    if (!stream) return fail(NDFB_E_INVALID, "null pointer");
+#ifdef NDFB_EMU
+    (void)device; *stream = nullptr; return 0;
+#else
+    DeviceGuard guard; (void)guard;
+    int rc = dev_set(device);
+    if (rc) return rc;
+    cudaStream_t s;
+    NDFB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return 0;
+#endif
+}
+void ndfb_stream_destroy(void* stream) {
+#ifndef NDFB_EMU
+    if (stream) cudaStreamDestroy((cudaStream_t)stream);
+#else
+    (void)stream;
+#endif
+}
+int ndfb_stream_sync(void* stream) { return dev_sync((stream_t)stream); }
+
 void ndfb_hint_next_launch_smem(size_t bytes) { launch_smem_floor() = bytes; }
 const char* ndfb_last_error(void) { return g_err.c_str(); }
 const char* ndfb_version(void) { return version_string(); }

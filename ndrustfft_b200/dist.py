@@ -51,7 +51,7 @@ class SlabR2cFft3d:
     """
 
     def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto",
-                 row_chunks=1, scatter_smem=None, blocked=True):
+                 row_chunks=1, scatter_smem=None, blocked=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist

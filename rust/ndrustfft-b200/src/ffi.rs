@@ -23,6 +23,9 @@ pub const NDFB_NORM_NONE: c_int = 0;
 pub const NDFB_NORM_DEFAULT: c_int = 1;
 pub const NDFB_MEM_HOST: c_int = 0;
 pub const NDFB_MEM_DEVICE: c_int = 1;
+pub const NDFB_COPY_H2D: c_int = 0;
+pub const NDFB_COPY_D2H: c_int = 1;
+pub const NDFB_COPY_D2D: c_int = 2;
 
 /// `struct ndfb_step` of the C header.
 #[repr(C)]
@@ -53,6 +56,13 @@ extern "C" {
         shape_in: *const usize, strides_in: *const isize, shape_out: *const usize, strides_out: *const isize,
         mem: c_int, stream: *mut c_void,
     ) -> c_int;
+    /// Device memory / stream helpers (include/ndfft_b200.h) behind `DeviceArray` and `Stream`.
+    pub fn ndfb_device_alloc(ptr: *mut *mut c_void, bytes: usize, device: c_int) -> c_int;
+    pub fn ndfb_device_free(ptr: *mut c_void);
+    pub fn ndfb_memcpy(dst: *mut c_void, src: *const c_void, bytes: usize, kind: c_int, device: c_int, stream: *mut c_void) -> c_int;
+    pub fn ndfb_stream_create(stream: *mut *mut c_void, device: c_int) -> c_int;
+    pub fn ndfb_stream_destroy(stream: *mut c_void);
+    pub fn ndfb_stream_sync(stream: *mut c_void) -> c_int;
     pub fn ndfb_last_error() -> *const c_char;
     pub fn ndfb_version() -> *const c_char;
 }

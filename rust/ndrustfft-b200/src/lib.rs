@@ -8,26 +8,44 @@
 //!
 //! This crate is source-only in the build image (no Rust toolchain there); see INTEGRATION.md.
 #![warn(missing_docs)]
+mod device;
 mod ffi;
 
+pub use device::{
+    fft2, ifft2, irfft2, ndchain, ndchain_dev, nddct_dev, ndfft_dev, ndfft_r2c_dev, ndifft_dev, ndifft_r2c_dev, rfft2, DeviceArray, Step, Stream,
+};
 use ndarray::{ArrayBase, Data, DataMut, Dimension};
-pub use num_complex::Complex;
 use num_traits::FloatConst;
-pub use num_traits::Zero;
+use std::any::TypeId;
 use std::ffi::CStr;
 use std::os::raw::{c_int, c_void};
 use std::sync::Arc;
 
-/// The two element types ndrustfft supports (`FftNum`, reference src/lib.rs:85, 111): `f32` and `f64`.
-pub trait FftNum: Copy + Send + Sync + 'static + FloatConst + num_traits::Float {
-    #[doc(hidden)]
-    const DTYPE: c_int;
-}
-impl FftNum for f32 {
-    const DTYPE: c_int = ffi::NDFB_F32;
-}
-impl FftNum for f64 {
-    const DTYPE: c_int = ffi::NDFB_F64;
+// The reference re-exports exactly these three names (src/lib.rs:83-85):
+//     pub use rustfft::FftNum;  pub use rustfft::num_complex::Complex;  pub use rustfft::num_traits::Zero;
+// With the `rustfft` feature the SAME trait object is re-exported, so code that is generic over `rustfft::FftNum`
+// keeps compiling; without it (the dependency-light default) a trait of the same name and the same supertraits as
+// rustfft 6's stands in.  The functions below bound `T: FftNum + FloatConst` exactly as the reference does (:111) and
+// find the element type at run time, so no extra bound leaks into callers' generic code.
+pub use num_complex::Complex;
+pub use num_traits::Zero;
+#[cfg(feature = "rustfft")]
+pub use rustfft::FftNum;
+/// Generic floating point number (`rustfft::FftNum`'s supertraits); implemented for `f32` and `f64`.
+#[cfg(not(feature = "rustfft"))]
+pub trait FftNum: Copy + num_traits::FromPrimitive + num_traits::Signed + Sync + Send + std::fmt::Debug + 'static {}
+#[cfg(not(feature = "rustfft"))]
+impl<T> FftNum for T where T: Copy + num_traits::FromPrimitive + num_traits::Signed + Sync + Send + std::fmt::Debug + 'static {}
+
+/// `NDFB_F32` / `NDFB_F64` for `T`; the reference supports exactly these two (`FftNum + FloatConst`, src/lib.rs:111).
+pub(crate) fn dtype_of<T: 'static>() -> c_int {
+    if TypeId::of::<T>() == TypeId::of::<f32>() {
+        ffi::NDFB_F32
+    } else if TypeId::of::<T>() == TypeId::of::<f64>() {
+        ffi::NDFB_F64
+    } else {
+        panic!("ndrustfft-b200 supports f32 and f64")
+    }
 }
 
 /// Represents different types of normalization methods (reference src/lib.rs:89-98).
@@ -41,7 +59,7 @@ pub enum Normalization<T> {
     Custom(fn(&mut [T])),
 }
 
-struct PlanHandle(*mut ffi::NdfbPlan);
+pub(crate) struct PlanHandle(pub(crate) *mut ffi::NdfbPlan);
 // The C plan is immutable after creation and internally synchronised (include/ndfft_b200.h).
 unsafe impl Send for PlanHandle {}
 unsafe impl Sync for PlanHandle {}
@@ -51,7 +69,7 @@ impl Drop for PlanHandle {
     }
 }
 
-fn last_error() -> String {
+pub(crate) fn last_error() -> String {
     unsafe { CStr::from_ptr(ffi::ndfb_last_error()).to_string_lossy().into_owned() }
 }
 
@@ -99,7 +117,7 @@ fn apply_lanes<T: Clone, S: DataMut<Elem = T>, D: Dimension>(f: fn(&mut [T]), ar
     }
 }
 
-fn norm_code<T>(n: &Normalization<T>) -> c_int {
+pub(crate) fn norm_code<T>(n: &Normalization<T>) -> c_int {
     match n {
         Normalization::Default => ffi::NDFB_NORM_DEFAULT,
         _ => ffi::NDFB_NORM_NONE,
@@ -111,15 +129,15 @@ fn norm_code<T>(n: &Normalization<T>) -> c_int {
 #[derive(Clone)]
 pub struct FftHandler<T> {
     n: usize,
-    plan: Arc<PlanHandle>,
-    norm: Normalization<Complex<T>>,
+    pub(crate) plan: Arc<PlanHandle>,
+    pub(crate) norm: Normalization<Complex<T>>,
 }
 
 impl<T: FftNum> FftHandler<T> {
     /// Creates a new `FftHandler` for transforms of length `n` (reference src/lib.rs:294-304).
     #[must_use]
     pub fn new(n: usize) -> Self {
-        Self { n, plan: new_plan(ffi::NDFB_C2C, T::DTYPE, n), norm: Normalization::Default }
+        Self { n, plan: new_plan(ffi::NDFB_C2C, dtype_of::<T>(), n), norm: Normalization::Default }
     }
     /// Modifies the normalization applied to the backward transform (reference src/lib.rs:308-311).
     #[must_use]
@@ -127,7 +145,9 @@ impl<T: FftNum> FftHandler<T> {
         self.norm = norm;
         self
     }
-    /// Transform length.
+    /// Transform length (not part of the reference's API).
+    #[doc(hidden)]
+    #[allow(clippy::len_without_is_empty)]
     pub fn len(&self) -> usize {
         self.n
     }
@@ -136,7 +156,7 @@ impl<T: FftNum> FftHandler<T> {
 /// Complex-to-complex Fourier Transform (reference src/lib.rs:350-372).
 pub fn ndfft<R, S, T, D>(input: &ArrayBase<R, D>, output: &mut ArrayBase<S, D>, handler: &FftHandler<T>, axis: usize)
 where
-    T: FftNum,
+    T: FftNum + FloatConst,
     R: Data<Elem = Complex<T>>,
     S: Data<Elem = Complex<T>> + DataMut,
     D: Dimension,
@@ -147,7 +167,7 @@ where
 /// Complex-to-complex inverse Fourier Transform (reference src/lib.rs:374-397).
 pub fn ndifft<R, S, T, D>(input: &ArrayBase<R, D>, output: &mut ArrayBase<S, D>, handler: &FftHandler<T>, axis: usize)
 where
-    T: FftNum,
+    T: FftNum + FloatConst,
     R: Data<Elem = Complex<T>>,
     S: Data<Elem = Complex<T>> + DataMut,
     D: Dimension,
@@ -164,15 +184,15 @@ where
 pub struct R2cFftHandler<T> {
     n: usize,
     m: usize,
-    plan: Arc<PlanHandle>,
-    norm: Normalization<Complex<T>>,
+    pub(crate) plan: Arc<PlanHandle>,
+    pub(crate) norm: Normalization<Complex<T>>,
 }
 
 impl<T: FftNum> R2cFftHandler<T> {
     /// Creates a new handler for real length `n`; the spectrum has `n / 2 + 1` entries (reference src/lib.rs:477-488).
     #[must_use]
     pub fn new(n: usize) -> Self {
-        Self { n, m: n / 2 + 1, plan: new_plan(ffi::NDFB_R2C, T::DTYPE, n), norm: Normalization::Default }
+        Self { n, m: n / 2 + 1, plan: new_plan(ffi::NDFB_R2C, dtype_of::<T>(), n), norm: Normalization::Default }
     }
     /// Modifies the normalization applied to the backward transform (reference src/lib.rs:492-495).
     #[must_use]
@@ -180,7 +200,8 @@ impl<T: FftNum> R2cFftHandler<T> {
         self.norm = norm;
         self
     }
-    /// (real length, spectrum length)
+    /// (real length, spectrum length) (not part of the reference's API).
+    #[doc(hidden)]
     pub fn lens(&self) -> (usize, usize) {
         (self.n, self.m)
     }
@@ -189,7 +210,7 @@ impl<T: FftNum> R2cFftHandler<T> {
 /// Real-to-complex Fourier Transform (reference src/lib.rs:543-564).
 pub fn ndfft_r2c<R, S, T, D>(input: &ArrayBase<R, D>, output: &mut ArrayBase<S, D>, handler: &R2cFftHandler<T>, axis: usize)
 where
-    T: FftNum,
+    T: FftNum + FloatConst,
     R: Data<Elem = T>,
     S: Data<Elem = Complex<T>> + DataMut,
     D: Dimension,
@@ -200,7 +221,7 @@ where
 /// Complex-to-real inverse Fourier Transform (reference src/lib.rs:566-587).
 pub fn ndifft_r2c<R, S, T, D>(input: &ArrayBase<R, D>, output: &mut ArrayBase<S, D>, handler: &R2cFftHandler<T>, axis: usize)
 where
-    T: FftNum,
+    T: FftNum + FloatConst,
     R: Data<Elem = Complex<T>>,
     S: Data<Elem = T> + DataMut,
     D: Dimension,
@@ -220,15 +241,15 @@ where
 #[derive(Clone)]
 pub struct DctHandler<T> {
     n: usize,
-    plan: Arc<PlanHandle>,
-    norm: Normalization<T>,
+    pub(crate) plan: Arc<PlanHandle>,
+    pub(crate) norm: Normalization<T>,
 }
 
 impl<T: FftNum> DctHandler<T> {
     /// Creates a new `DctHandler` (reference src/lib.rs:665-679); the four schedules are built lazily on first use.
     #[must_use]
     pub fn new(n: usize) -> Self {
-        Self { n, plan: new_plan(ffi::NDFB_DCT, T::DTYPE, n), norm: Normalization::Default }
+        Self { n, plan: new_plan(ffi::NDFB_DCT, dtype_of::<T>(), n), norm: Normalization::Default }
     }
     /// Modifies the normalization (reference src/lib.rs:683-686).
     #[must_use]
@@ -236,7 +257,9 @@ impl<T: FftNum> DctHandler<T> {
         self.norm = norm;
         self
     }
-    /// Transform length.
+    /// Transform length (not part of the reference's API).
+    #[doc(hidden)]
+    #[allow(clippy::len_without_is_empty)]
     pub fn len(&self) -> usize {
         self.n
     }
@@ -244,7 +267,7 @@ impl<T: FftNum> DctHandler<T> {
 
 fn dct<R, S, T, D>(op: c_int, input: &ArrayBase<R, D>, output: &mut ArrayBase<S, D>, handler: &DctHandler<T>, axis: usize)
 where
-    T: FftNum,
+    T: FftNum + FloatConst,
     R: Data<Elem = T>,
     S: Data<Elem = T> + DataMut,
     D: Dimension,
@@ -263,7 +286,7 @@ macro_rules! dct_fn {
         $(#[$m])*
         pub fn $name<R, S, T, D>(input: &ArrayBase<R, D>, output: &mut ArrayBase<S, D>, handler: &DctHandler<T>, axis: usize)
         where
-            T: FftNum,
+            T: FftNum + FloatConst,
             R: Data<Elem = T>,
             S: Data<Elem = T> + DataMut,
             D: Dimension,
