@@ -189,6 +189,16 @@ NDFB_API int ndfb_jit_compile_check(int dtype, int rkind, size_t core_n, int col
  * (e.g. 116 KiB => one CTA per SM), so that a link-bound kernel leaves room for another stream's HBM-bound kernel. */
 NDFB_API void ndfb_hint_next_launch_smem(size_t bytes);
 
+/* Producer / consumer overlap of two calls issued on DIFFERENT streams (no event between them): the next real-kind
+ * fast-path launch of the calling thread (ndfft_r2c ...) adds the number of lanes of every finished tile to
+ * counters[first_lane / lanes_per_group] (32-bit, zeroed by the caller); the next ndfft / ndifft launch on strided
+ * columns runs as `ctas_per_sm` persistent CTAs per SM and loads a tile only after counters[first_lane / lanes_per_group]
+ * has reached `need`.  Lane indices count the non-transformed elements in memory order of the INPUT of the respective
+ * call.  dist.SlabR2cFft3d uses the pair to start the exchange pass on plane p as soon as plane p's r2c rows are done.
+ * A call that cannot honour a pending hint returns NDFB_E_UNSUPPORTED (the consumer waits are bounded: no hang). */
+NDFB_API void ndfb_hint_next_launch_signal(void* counters, long long lanes_per_group);
+NDFB_API void ndfb_hint_next_launch_wait(const void* counters, long long lanes_per_group, unsigned need, int ctas_per_sm);
+
 /* Release cached workspaces / pinned staging buffers held by the calling thread's pools. */
 NDFB_API void ndfb_release_workspaces(void);
 

@@ -27,7 +27,7 @@ EXPORTS = (
     "ndfb_plan_create", "ndfb_plan_destroy", "ndfb_plan_describe", "ndfb_exec", "ndfb_exec_scaled", "ndfb_exec_split_out", "ndfb_exec_scatter_out",
     "ndfb_exec_chain", "ndfb_jit_compile_check",
     "ndfb_device_alloc", "ndfb_device_free", "ndfb_memcpy", "ndfb_stream_create", "ndfb_stream_destroy", "ndfb_stream_sync",
-    "ndfb_hint_next_launch_smem", "ndfb_last_error", "ndfb_version", "ndfb_launch_count", "ndfb_release_workspaces",
+    "ndfb_hint_next_launch_smem", "ndfb_hint_next_launch_signal", "ndfb_hint_next_launch_wait", "ndfb_last_error", "ndfb_version", "ndfb_launch_count", "ndfb_release_workspaces",
 )
 
 
@@ -92,6 +92,10 @@ class CLib:
         d.ndfb_stream_sync.restype = ci
         d.ndfb_hint_next_launch_smem.argtypes = [cz]
         d.ndfb_hint_next_launch_smem.restype = None
+        d.ndfb_hint_next_launch_signal.argtypes = [vp, ctypes.c_longlong]
+        d.ndfb_hint_next_launch_signal.restype = None
+        d.ndfb_hint_next_launch_wait.argtypes = [vp, ctypes.c_longlong, ctypes.c_uint, ci]
+        d.ndfb_hint_next_launch_wait.restype = None
         d.ndfb_last_error.restype = ctypes.c_char_p
         d.ndfb_version.restype = ctypes.c_char_p
         d.ndfb_launch_count.restype = ctypes.c_uint64

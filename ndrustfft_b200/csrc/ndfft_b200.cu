@@ -34,6 +34,13 @@ static std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t>& launch_counter() { return g_launches; }
 static thread_local size_t g_smem_floor = 0;
 size_t& launch_smem_floor() { return g_smem_floor; }
+// producer / consumer hints for the NEXT fast-path launch of this thread (ndfb_hint_next_launch_signal / _wait)
+struct SyncHint {
+    unsigned* signal_cnt = nullptr; long long signal_group = 0;
+    const unsigned* wait_cnt = nullptr; long long wait_group = 0; unsigned wait_need = 0; int ctas_per_sm = 0;
+    void clear() { *this = SyncHint(); }
+};
+static thread_local SyncHint g_sync_hint;
 
 // ------------------------------------------------------------------------------------------------------
 // plans
@@ -505,8 +512,19 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
         a.bulk_store = aligned ? 1 : 0;
     }
     if (a.bulk_store && std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] scatter blocks as bulk-async copies: %d x %zu bytes per tile\n", s.nblk_ptr, (size_t)s.os_blk * e->L * sizeof(Cx<R>));
-    const long long grid = (nlanes + e->L - 1) / e->L;
+    long long grid = (nlanes + e->L - 1) / e->L;
     if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+    if (g_sync_hint.wait_cnt) {
+        // consumer of another launch's output: persistent CTAs that wait for their tile's producer group
+        const SyncHint h = g_sync_hint;
+        g_sync_hint.clear();
+        if (!(e->cols && e->r[1] > 1 && e->N >= 64 && e->N <= 2048) || s.fs_twiddle || h.wait_group % e->L)
+            return fail(NDFB_E_UNSUPPORTED, "launch wait hint: this transform has no persistent consumer kernel");
+        a.wait_cnt = h.wait_cnt; a.wait_group = h.wait_group; a.wait_need = h.wait_need;
+        a.ntiles = grid;
+        grid = std::min<long long>(grid, (long long)dev_sm_count(p->device) * std::max(1, h.ctas_per_sm));
+        if (std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] persistent consumer launch: %lld tiles on %lld CTAs\n", a.ntiles, grid);
+    }
     if (e->jit_func) return jit_launch(e->jit_func, a, (unsigned)grid, (unsigned)e->threads, e->smem, stream);
     return e->launch(a, (unsigned)grid, stream);
 }
@@ -680,6 +698,12 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             a.tw = twd;
             const long long grid = (nlanes + e->L - 1) / e->L;
             if (grid > 0x7fffffffLL) return fail(NDFB_E_UNSUPPORTED, "too many tiles");
+            if (g_sync_hint.signal_cnt) {
+                const SyncHint h = g_sync_hint;
+                g_sync_hint.clear();
+                if (h.signal_group % e->L) return fail(NDFB_E_UNSUPPORTED, "launch signal hint: group size is not a multiple of the tile width");
+                a.done_cnt = h.signal_cnt; a.done_group = h.signal_group;
+            }
             if (e->jit_func) return jit_launch(e->jit_func, a, (unsigned)grid, (unsigned)e->threads, e->smem, stream);
             return e->launch(a, (unsigned)grid, stream);
         }
@@ -1743,9 +1767,14 @@ static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_sca
     for (int d = 0; d < ndim; ++d) if (shape_in[d] == 0 || shape_out[d] == 0) empty = true;
     if (empty) return NDFB_OK;
     if (!in || !out) return fail(NDFB_E_INVALID, "null data pointer");
-    if (p->dtype == NDFB_F32)
-        return exec_any<float>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
-    return exec_any<double>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+    rc = p->dtype == NDFB_F32
+             ? exec_any<float>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream)
+             : exec_any<double>(p, o, extra_scale, in, out, ndim, shape_in, strides_in, shape_out, strides_out, axis, mem, stream);
+    if (g_sync_hint.signal_cnt || g_sync_hint.wait_cnt) {   // the call took a path that cannot honour the hint: say so
+        g_sync_hint.clear();
+        if (!rc) rc = fail(NDFB_E_UNSUPPORTED, "launch signal / wait hint was not consumed by this call");
+    }
+    return rc;
 }
 
 int ndfb_exec_split_out(const ndfb_plan* plan, int op, int norm, double extra_scale, size_t out_block, ptrdiff_t out_block_stride,
@@ -1933,6 +1962,13 @@ void ndfb_stream_destroy(void* stream) {
 int ndfb_stream_sync(void* stream) { return dev_sync((stream_t)stream); }
 
 void ndfb_hint_next_launch_smem(size_t bytes) { launch_smem_floor() = bytes; }
+void ndfb_hint_next_launch_signal(void* counters, long long lanes_per_group) {
+    g_sync_hint.signal_cnt = (unsigned*)counters; g_sync_hint.signal_group = lanes_per_group > 0 ? lanes_per_group : 1;
+}
+void ndfb_hint_next_launch_wait(const void* counters, long long lanes_per_group, unsigned need, int ctas_per_sm) {
+    g_sync_hint.wait_cnt = (const unsigned*)counters; g_sync_hint.wait_group = lanes_per_group > 0 ? lanes_per_group : 1;
+    g_sync_hint.wait_need = need; g_sync_hint.ctas_per_sm = ctas_per_sm;
+}
 const char* ndfb_last_error(void) { return g_err.c_str(); }
 const char* ndfb_version(void) { return version_string(); }
 uint64_t ndfb_launch_count(void) { return g_launches.load(); }

@@ -36,6 +36,13 @@ struct SfftArgs {
     long long os_blk_stride;  // ... with this stride for the block index (packed all-to-all send layout)
     int nblk_ptr;          // != 0: block p is written relative to blk_ptr[p] (peer-mapped receive buffers: the store IS the all-to-all)
     void* blk_ptr[8];
+    // Producer / consumer overlap between two launches on different streams (dist.SlabR2cFft3d: the r2c pass feeds the
+    // exchange pass plane by plane).  Consumer side: before tile t is loaded, wait until wait_cnt[first lane / wait_group]
+    // has reached wait_need (the producer adds the lanes it has finished); the launch is persistent (tiles strided by gridDim).
+    const unsigned* wait_cnt;
+    long long wait_group;
+    unsigned wait_need;
+    long long ntiles;      // persistent launches: total number of tiles (0 = one tile per CTA)
     int bulk_store;        // != 0 (with nblk_ptr): the tile's block for each destination is one contiguous range there: stage the result
                            // in shared memory and send each block with ONE bulk-async copy (cp.async.bulk, the TMA engine)
     const void* fs_lo;
@@ -309,7 +316,7 @@ NDFB_DEV void bulk_store_commit_and_drain() {
 // MODE 0: plain store;  1: four-step twiddle from the single table W_N^e (N <= 2^17), nothing else;  2: everything
 // (hi/lo twiddle product, split / scattered output blocks).  UNIT: both axis strides are 1 (contiguous rows)
 template <typename R, class S, int L, bool COLS, int MODE, bool UNIT, bool CG = false>
-NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, const LaneBase& lb) {
+NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, const LaneBase& lb, long long tile = 0) {
     const Cx<R>* __restrict__ in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi;
     Cx<R>* __restrict__ out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo;
     const long long is_axis = UNIT ? 1 : a.is_axis, os_axis = UNIT ? 1 : a.os_axis;
@@ -344,7 +351,7 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
         bulk_store_fence();                         // every writer: its stores become visible to the async proxy ...
         __syncthreads();                            // ... and the issuing threads are ordered after all of them
         if (threadIdx.x < (unsigned)a.nblk_ptr) {   // thread p sends block p (only lane 0's base is used)
-            const LaneBase lb0 = lane_base(a, (long long)blockIdx.x * L, true, 0);
+            const LaneBase lb0 = lane_base(a, tile * L, true, 0);
             const int p = (int)threadIdx.x;
             bulk_store_issue(reinterpret_cast<Cx<R>*>(a.blk_ptr[p]) + lb0.bo, c.smem + (size_t)p * a.os_blk * L,
                              (unsigned)(sizeof(Cx<R>) * (size_t)a.os_blk * L));
@@ -377,6 +384,26 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
 }
 
+NDFB_DEV unsigned sync_ld_acquire(const unsigned* p) {
+#ifdef NDFB_EMU
+    return *p;
+#else
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+// bounded poll by one thread (a logic error or a lost producer must not hang the GPU: after ~1 s the consumer goes on)
+NDFB_DEV void sync_wait_ge(const unsigned* counter, unsigned need) {
+    unsigned spins = 0;
+    while (sync_ld_acquire(counter) < need) {
+#ifndef NDFB_EMU
+        __nanosleep(128);
+#endif
+        if (++spins > (1u << 23)) break;
+    }
+}
+
 // lengths whose column kernels carry the bulk-async scatter epilogue (the axis lengths a slab exchange splits; keeping the
 // variant out of the other ~400 column instances keeps the library and its build time down)
 template <class S, bool COLS>
@@ -390,16 +417,35 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     const int tid = threadIdx.x;
     if (COLS) { c.l = tid % L; c.i = tid / L; }
     else { c.i = tid % S::TL; c.l = tid / S::TL; }
+    const bool plain = !a.fs_twiddle && !a.os_blk;
+    if constexpr (kSfftBulkStore<S, COLS>) {
+        if (a.ntiles) {
+            // persistent consumer of another launch's output (see SfftArgs::wait_cnt): a few CTAs per SM walk the tiles
+            for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                if (a.wait_cnt) {
+                    if (tid == 0) sync_wait_ge(&a.wait_cnt[(tile * L) / a.wait_group], a.wait_need);
+                    __syncthreads();
+                }
+                const long long g = tile * L + c.l;
+                c.valid = g < a.nlanes;
+                const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
+                if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb, tile);
+                else if (a.bulk_store) sfft_body<R, S, L, COLS, 3, false>(a, c, lb, tile);
+                else sfft_body<R, S, L, COLS, 2, false>(a, c, lb, tile);
+                __syncthreads();     // the shared buffer is reused by the next tile
+            }
+            return;
+        }
+    }
     const long long g = (long long)blockIdx.x * L + c.l;
     c.valid = g < a.nlanes;
     const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
-    const bool plain = !a.fs_twiddle && !a.os_blk;
-    if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, 0, true>(a, c, lb);
-    else if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb);
-    else if (a.fs_twiddle && a.fs_shift >= 40 && !a.os_blk) sfft_body<R, S, L, COLS, 1, false>(a, c, lb);
+    if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, 0, true>(a, c, lb, blockIdx.x);
+    else if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb, blockIdx.x);
+    else if (a.fs_twiddle && a.fs_shift >= 40 && !a.os_blk) sfft_body<R, S, L, COLS, 1, false>(a, c, lb, blockIdx.x);
     else if (kSfftBulkStore<S, COLS> && a.bulk_store) {
-        if constexpr (kSfftBulkStore<S, COLS>) sfft_body<R, S, L, COLS, 3, false>(a, c, lb);
-    } else sfft_body<R, S, L, COLS, 2, false>(a, c, lb);
+        if constexpr (kSfftBulkStore<S, COLS>) sfft_body<R, S, L, COLS, 3, false>(a, c, lb, blockIdx.x);
+    } else sfft_body<R, S, L, COLS, 2, false>(a, c, lb, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -604,6 +650,8 @@ struct RsfftArgs {
     int n;            // logical (real) length
     double scale;
     const void* tw;   // per-pass twiddle tables
+    unsigned* done_cnt;     // producer side of SfftArgs::wait_cnt: done_cnt[first lane / done_group] += lanes of this tile, after its stores
+    long long done_group;
     const void* tabA; // exp(-2 pi i k / (2N)), k <= N   (DCT-IV: exp(-i pi j / n))
     const void* tabB; // DCT-II/III: exp(-i pi k / (2n));  DCT-IV: exp(-i pi (4j+1) / (4n))
 };
@@ -821,12 +869,25 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     }
 }
 
+// release of a finished tile to a consumer launch: every thread's stores are ordered before the counter update
+NDFB_DEV void rsfft_signal(const RsfftArgs& a, int L) {
+    if (!a.done_cnt) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const long long g0 = (long long)blockIdx.x * L;
+        const long long left = a.nlanes - g0;
+        atomicAdd(&a.done_cnt[g0 / a.done_group], (unsigned)(left < L ? left : L));
+    }
+}
+
 template <typename R, class S, int L, bool COLS, int KIND, int MINB>
 __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_constant__ RsfftArgs a) {
     if constexpr (!COLS) {
-        if (a.is_axis == 1 && a.os_axis == 1) { rsfft_body<R, S, L, COLS, KIND, true>(a); return; }
+        if (a.is_axis == 1 && a.os_axis == 1) { rsfft_body<R, S, L, COLS, KIND, true>(a); rsfft_signal(a, L); return; }
     }
     rsfft_body<R, S, L, COLS, KIND, false>(a);
+    rsfft_signal(a, L);
 }
 
 }  // namespace ndfb

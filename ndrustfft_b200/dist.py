@@ -51,7 +51,7 @@ class SlabR2cFft3d:
     """
 
     def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto",
-                 row_chunks=1, scatter_smem=None, blocked=False):
+                 row_chunks=1, scatter_smem=None, blocked=False, overlap=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -78,6 +78,7 @@ class SlabR2cFft3d:
         lanes128 = 128 // (8 if self.rdt == np.float32 else 16)
         self.lanes128 = lanes128
         self.blocked = bool(blocked)
+        self.overlap = bool(overlap)
         self.mp = -(-self.m // lanes128) * lanes128
         self.a_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
         self.b_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
@@ -111,6 +112,8 @@ class SlabR2cFft3d:
                 kp = min(kp, units)
                 self.pchunks = [tuple(lanes128 * v for v in shard_bounds(units, kp, c)) for c in range(kp)]
                 self._s1, self._s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+                self._cnt = torch.zeros(self.s0, dtype=torch.int32, device=self.device)
+                self.consumer_ctas = 1
                 self._ev = [torch.cuda.Event() for _ in range(max(kp, int(row_chunks)) + 1)]
                 # row-chunked overlap: r2c of row chunk c+1 (HBM-bound) runs beside the scatter of chunk c (NVLink-bound);
                 # the scatter launch is capped to ~1 CTA/SM through a shared-memory floor so the other stream gets SM room
@@ -140,7 +143,8 @@ class SlabR2cFft3d:
         padded_out = out is None
         if padded_out:
             out = self.out_pad[:, :, :self.m]                   # a view of the library-owned padded result
-        if not (P > 1 and self.peer and len(self.pchunks) == 1 and len(self.rchunks) > 1):
+        fused_feed = P > 1 and self.peer and self.overlap and len(self.pchunks) == 1 and len(self.rchunks) == 1
+        if not (P > 1 and self.peer and len(self.pchunks) == 1 and len(self.rchunks) > 1) and not fused_feed:
             be.ndfft_r2c(x, self.a, self.h2, 2)
         if P == 1:
             be.ndfft(self.a_pad, self.b_pad, self.h1, 1)        # padded lanes: 264 per row, tiles never straddle rows
@@ -176,6 +180,28 @@ class SlabR2cFft3d:
                 with t.cuda.stream(self._s2):
                     hdl.barrier()
                 main.wait_stream(self._s2)
+                if padded_out:
+                    be.ndfft(recv, self.out_pad, self.h0, 0)
+                else:
+                    be.ndfft(recv[:, :, :self.m], out, self.h0, 0)
+                return out
+            if fused_feed:
+                # r2c pass and exchange pass run CONCURRENTLY on two streams: the r2c kernel counts finished rows per plane,
+                # the exchange kernel (one persistent CTA per SM, so r2c CTAs always find room) starts on plane p as soon
+                # as its 512 rows are there.  The NVLink-bound exchange thereby hides the HBM-bound r2c pass.
+                main = t.cuda.current_stream(self.device)
+                cnt = self._cnt
+                cnt.zero_()
+                self._s1.wait_stream(main)
+                dll = be.lib.dll
+                dll.ndfb_hint_next_launch_signal(cnt.data_ptr(), n1)
+                be.ndfft_r2c(x, self.a, self.h2, 2)
+                with t.cuda.stream(self._s1):
+                    dll.ndfb_hint_next_launch_wait(cnt.data_ptr(), mp, n1, self.consumer_ctas)
+                    be.ndfft_scatter_out(self.a_pad, self.h1, 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1),
+                                         out_block=s1, block_ptrs=ptrs)
+                    hdl.barrier()
+                main.wait_stream(self._s1)
                 if padded_out:
                     be.ndfft(recv, self.out_pad, self.h0, 0)
                 else:

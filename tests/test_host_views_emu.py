@@ -209,3 +209,36 @@ def test_bulk_async_scatter_blocks(be, capfd):
                              out_block=s1, block_ptrs=[b.ctypes.data for b in b2])
     for d in range(P):
         assert np.array_equal(b2[d], bufs[d])
+
+
+def test_signal_and_wait_hints(be, capfd):
+    """Producer / consumer launch hints (ndfb_hint_next_launch_signal / _wait): the r2c pass counts finished rows per plane,
+    the persistent exchange pass waits per plane.  Under the emulator launches run one after the other, so every wait is
+    already satisfied; the counters, the persistent tile loop and the results are what is checked."""
+    rng = np.random.default_rng(8)
+    s0, n1, n2 = 3, 64, 128
+    m = n2 // 2 + 1
+    mp = 80
+    x = rng.uniform(-1, 1, (s0, n1, n2))
+    a_pad = np.zeros((s0, n1, mp), complex)
+    cnt = np.zeros(s0, np.uint32)
+    dll = be.lib.dll
+    dll.ndfb_hint_next_launch_signal(cnt.ctypes.data, n1)
+    be.ndfft_r2c(x, a_pad[:, :, :m], be.R2cFftHandler(n2), 2)
+    # host arrays with gaps are packed first: the counters still count every row of every plane
+    assert cnt.tolist() == [n1] * s0
+    P, s1 = 2, n1 // 2
+    bufs = [np.zeros((s0, s1, mp), complex) for _ in range(P)]
+    with _env(NDFB_TRACE=1):
+        dll.ndfb_hint_next_launch_wait(cnt.ctypes.data, mp, n1, 1)
+        be.ndfft_scatter_out(a_pad, be.FftHandler(n1), 1, out_shape=(s0, n1, mp), out_strides=(s1 * mp, mp, 1), out_block=s1,
+                             block_ptrs=[b.ctypes.data for b in bufs])
+    assert "persistent consumer launch" in capfd.readouterr().err
+    want = np.fft.fft(np.fft.rfft(x, axis=2), axis=1)
+    for p in range(P):
+        assert orc.rel_l2(bufs[p][:, :, :m], want[:, p * s1:(p + 1) * s1, :]) < 1e-12
+    # a call that cannot honour the hint says so
+    dll.ndfb_hint_next_launch_wait(cnt.ctypes.data, mp, n1, 1)
+    y = np.zeros((4, 17), complex)
+    with pytest.raises(Exception, match="hint"):
+        be.ndfft(np.zeros((4, 17), complex), y, be.FftHandler(17), 1)

@@ -12,7 +12,9 @@ ap.add_argument("--chunks", default="1,2,4,8")
 ap.add_argument("--graph", default="0,1")
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--phases", type=int, default=1)
-ap.add_argument("--blocked", default="1,0")
+ap.add_argument("--blocked", default="0")
+ap.add_argument("--overlap", default="1,0")
+ap.add_argument("--ctas", default="1")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -52,7 +54,7 @@ g = torch.Generator(device=dev); g.manual_seed(0xB200 + 48 + rank)
 x = torch.rand((n // world, n, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
 
 if a.phases and world > 1:
-    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=1)
+    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=1, overlap=False)
     be = plan.be
     for _ in range(3):
         plan.forward(x)
@@ -76,10 +78,11 @@ if a.phases and world > 1:
     emit(ph)
     del plan
 
-for chunks, blocked in [(int(v), int(b)) for v in a.chunks.split(",") for b in a.blocked.split(",")]:
-    if (world == 1 and chunks > 1) or (chunks > 1 and blocked):
+for chunks, blocked, overlap, ctas in [(int(v), int(b), int(o), int(c)) for v in a.chunks.split(",") for b in a.blocked.split(",") for o in a.overlap.split(",") for c in a.ctas.split(",")]:
+    if (world == 1 and chunks > 1) or (chunks > 1 and (blocked or overlap)) or (not overlap and ctas != int(a.ctas.split(",")[0])):
         continue
-    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=chunks, blocked=bool(blocked))
+    plan = SlabR2cFft3d((n, n, n), np.float64, device=dev, chunks=chunks, blocked=bool(blocked), overlap=bool(overlap))
+    plan.consumer_ctas = ctas
     for _ in range(3):
         out = plan.forward(x)
     back = plan.inverse(out)
@@ -103,7 +106,7 @@ for chunks, blocked in [(int(v), int(b)) for v in a.chunks.split(",") for b in a
                 emit({"chunks": chunks, "graph": 1, "error": repr(e)[:300]})
                 continue
         ms = timed(run, a.steps, per)
-        emit({"cfg": "c3", "n_gpus": world, "chunks": chunks, "blocked": bool(blocked), "cuda_graph": bool(graph), "ms": ms, "GFLOP/s": FLOPS / (ms * 1e-3) / 1e9,
+        emit({"cfg": "c3", "n_gpus": world, "chunks": chunks, "blocked": bool(blocked), "overlap": bool(overlap), "consumer_ctas": ctas, "cuda_graph": bool(graph), "ms": ms, "GFLOP/s": FLOPS / (ms * 1e-3) / 1e9,
               "peer": bool(getattr(plan, "peer", False)), "roundtrip_rel_l2": rel,
               "nvlink_ms_at_770": plan.bytes_sent_per_rank() / 770e9 * 1e3 if world > 1 else 0.0})
     del plan
