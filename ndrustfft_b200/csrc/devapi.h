@@ -50,6 +50,11 @@ inline int dev_sm_count(int) { return 148; }
 template <typename K, typename A>
 inline int dev_launch(K kernel, unsigned grid, unsigned block, size_t smem, stream_t, const A& a) {
     A copy = a;
+    {
+        size_t& floor_ = launch_smem_floor();   // same occupancy / extra-room hint as the CUDA build
+        if (floor_ > smem) smem = floor_;
+        floor_ = 0;
+    }
     simt::launch(dim3(grid), dim3(block), smem, [&]() { kernel(copy); });
     launch_counter()++;
     return 0;

@@ -41,6 +41,7 @@ struct SyncHint {
     void clear() { *this = SyncHint(); }
 };
 static thread_local SyncHint g_sync_hint;
+static thread_local bool g_trans_next = false;   // launch_c2c -> launch_sfft: run the entry as a transposing rows kernel
 
 // ------------------------------------------------------------------------------------------------------
 // plans
@@ -235,6 +236,7 @@ struct LaunchSpec {
     void* blk_ptr[8] = {nullptr};
     ndfb_plan::FsTw fs;
     bool keep_dim_order = false;
+    bool trans = false;   // last pass of a three-pass split: contiguous lanes in, lane-interleaved out (sfft_body_trans)
     int max_L = 0;    // != 0: widest tile allowed (transposing passes want 32/L points of a lane per warp >= one sector)
 };
 
@@ -481,6 +483,8 @@ static int get_sfft_twiddles(ndfb_plan* p, Core* c, const SfftEntry* e, void** o
 
 template <typename R>
 static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, stream_t stream) {
+    const bool trans_next = g_trans_next;
+    g_trans_next = false;
     SfftArgs a;
     std::memset(&a, 0, sizeof a);
     a.in = s.in; a.out = s.out;
@@ -502,6 +506,7 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     a.os_blk = s.os_blk; a.os_blk_stride = s.os_blk_stride;
     a.nblk_ptr = s.nblk_ptr;
     for (int i = 0; i < 8; ++i) a.blk_ptr[i] = s.blk_ptr[i];
+    a.trans_store = trans_next ? 1 : 0;
     // Scattered blocks that are contiguous per (tile, destination) go out as bulk-async copies (sfft_body MODE 3): column tile
     // over the fastest batch dim, that dim contiguous in the output and a whole number of tiles long, rows of a block L apart.
     if (s.nblk_ptr && e->cols && e->r[1] > 1 && e->N >= 64 && e->N <= 2048 && !s.fs_twiddle && !s.dims.empty() && s.dims[0].os == 1 && s.dims[0].size % e->L == 0 &&
@@ -556,6 +561,18 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         const bool have_batch = !s.dims.empty() && nlanes > 1;
         const bool cols = have_batch && t.N > 1 &&
                           (llabs_(s.dims[0].is) < llabs_(s.is_axis) || llabs_(s.dims[0].os) < llabs_(s.os_axis));
+        if (s.trans && s.is_axis == 1 && !s.dims.empty() && s.dims[0].os == 1 && !s.fs_twiddle && !s.os_blk) {
+            const SfftEntry* et = find_sfft(sizeof(R) == 8, t.N, false, nlanes);
+            if (!et && nlanes > 0) et = jit_entry<SfftEntry>(sizeof(R) == 8, -1, t.N, false, nlanes);
+            if (et && et->r[1] > 1 && et->L > 1) {
+                if (std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] sfft %s N=%d rows->lanes (transposing) L=%d T=%d lanes=%lld\n", sizeof(R) == 8 ? "f64" : "f32", et->N, et->L, et->threads, nlanes);
+                LaunchSpec st = s;
+                st.trans = false;
+                launch_smem_floor() = et->smem + (size_t)et->L * sizeof(Cx<R>) * 16;   // room for the padded lane pitch
+                g_trans_next = true;
+                return launch_sfft<R>(p, et, st, stream);
+            }
+        }
         const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>), s.max_L);
         if (!e && s.max_L) e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
         if (!e && nlanes > 0) e = jit_entry<SfftEntry>(sizeof(R) == 8, -1, t.N, cols, nlanes);
@@ -956,6 +973,9 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
         if (best != 0) {
             std::swap(s2.dims[0], s2.dims[best]);
             s2.max_L = sizeof(R) == 8 ? 16 : 8;
+            // preferred: the transposing rows kernel (full rows in, L adjacent output elements per store); the capped column
+            // tile above remains the fallback when there is no multi-pass row schedule for N2
+            s2.trans = !std::getenv("NDFB_NO_TRANS_STORE");
         }
     }
     {

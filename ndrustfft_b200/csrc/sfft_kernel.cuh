@@ -43,6 +43,8 @@ struct SfftArgs {
     long long wait_group;
     unsigned wait_need;
     long long ntiles;      // persistent launches: total number of tiles (0 = one tile per CTA)
+    int trans_store;       // != 0 (row kernels): the tile's lanes are far apart in the input but ADJACENT in the output (last pass of a
+                           // three-pass split): rows are read along the axis, the last pass re-maps threads so that stores run across lanes
     int bulk_store;        // != 0 (with nblk_ptr): the tile's block for each destination is one contiguous range there: stage the result
                            // in shared memory and send each block with ONE bulk-async copy (cp.async.bulk, the TMA engine)
     const void* fs_lo;
@@ -81,17 +83,20 @@ struct Sched {
     }
 };
 
-template <typename R, class S, int L, bool COLS>
+// PX: extra elements in the lane pitch of the row layout (transposing rows kernel: lanes become the fastest thread index in
+// the last pass, so the pitch must not be a multiple of the bank count)
+template <typename R, class S, int L, bool COLS, int PX = 0>
 struct SfftCtx {
     Cx<R>* smem;
     int i, l;  // position within the lane group, lane within the tile
     bool valid;
+    static constexpr int kPitch = S::NPAD + PX;
     NDFB_DEV int addr(int a) const {
         const int p = S::pad(a);
-        return COLS ? p * L + l : l * S::NPAD + p;
+        return COLS ? p * L + l : l * kPitch + p;
     }
     // slot of padded position `pp` (already padded)
-    NDFB_DEV int slot_of(int pp) const { return COLS ? pp * L + l : l * S::NPAD + pp; }
+    NDFB_DEV int slot_of(int pp) const { return COLS ? pp * L + l : l * kPitch + pp; }
     static constexpr int kscale = COLS ? L : 1;   // slot distance of one padded position
 };
 
@@ -153,8 +158,8 @@ struct SfftPass {
     static constexpr bool FW = !LAST && S::fast_write(PASS);
     static constexpr bool KCONST = !FIRST && (S::TL % P == 0);   // k = b mod P does not depend on m
 
-    template <typename LoadF, typename StoreF>
-    static NDFB_DEV void run(const SfftCtx<R, S, L, COLS>& c, Cx<R> (&v)[S::E], const Cx<R>* __restrict__ tw,
+    template <class Ctx, typename LoadF, typename StoreF>
+    static NDFB_DEV void run(const Ctx& c, Cx<R> (&v)[S::E], const Cx<R>* __restrict__ tw,
                              LoadF load, StoreF store) {
         // ---- gather this thread's butterfly inputs ----
         const int rbase = FR ? c.slot_of(S::pad(c.i)) : 0;
@@ -234,8 +239,8 @@ struct SfftPass {
 
 template <typename R, class S, int L, bool COLS, int PASS, bool SYNC0, bool SYNCL>
 struct SfftAll {
-    template <typename LoadF, typename StoreF>
-    static NDFB_DEV void run(const SfftCtx<R, S, L, COLS>& c, Cx<R> (&v)[S::E], const Cx<R>* tw, LoadF load, StoreF store) {
+    template <class Ctx, typename LoadF, typename StoreF>
+    static NDFB_DEV void run(const Ctx& c, Cx<R> (&v)[S::E], const Cx<R>* tw, LoadF load, StoreF store) {
         SfftPass<R, S, L, COLS, PASS, SYNC0, SYNCL>::run(c, v, tw, load, store);
         if constexpr (PASS + 1 < S::NP) SfftAll<R, S, L, COLS, PASS + 1, SYNC0, SYNCL>::run(c, v, tw, load, store);
     }
@@ -384,6 +389,51 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, load, store);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// transposing rows: contiguous lanes in, lane-interleaved out.  out[k1 + N1 k] of the LAST pass of a three-pass split
+// (2^24 = 256 x 256 x 256): the lanes k1 of a tile are 2 KiB-long contiguous rows in the workspace, N2 N3 elements apart,
+// and adjacent elements of the output.  Passes 0 .. NP-2 use the row mapping (threads along the axis: coalesced reads);
+// for the last pass the threads are re-dealt with the LANE as the fastest index, so every store instruction writes L
+// adjacent output elements.  The exchange between the two mappings is the ordinary shared-memory exchange of the
+// schedule; only the lane pitch is padded (PX) so that lane-strided reads of the last pass are conflict free.
+// ------------------------------------------------------------------------------------------------------
+template <class S, int W>   // W = 32-bit words per element
+constexpr int sfft_trans_px() {
+    int px = 0;
+    while (((S::NPAD + px) * W) % 32 != W % 32) ++px;
+    return px;
+}
+template <typename R, class S, int L, int PASS, class CtxA, class CtxB, class LoadF, class StoreF>
+NDFB_DEV void sfft_trans_passes(const CtxA& c, const CtxB& c2, Cx<R> (&v)[S::E], const Cx<R>* tw, LoadF load, StoreF store) {
+    if constexpr (PASS == S::NP - 1) {
+        SfftPass<R, S, L, false, PASS, false, false>::run(c2, v, tw, load, store);
+    } else {
+        SfftPass<R, S, L, false, PASS, false, false>::run(c, v, tw, load, store);
+        sfft_trans_passes<R, S, L, PASS + 1>(c, c2, v, tw, load, store);
+    }
+}
+template <typename R, class S, int L>
+NDFB_DEV void sfft_body_trans(const SfftArgs& a, long long tile) {
+    constexpr int PX = sfft_trans_px<S, (int)(sizeof(Cx<R>) / 4)>();
+    NDFB_DYN_SMEM(smem_raw);
+    SfftCtx<R, S, L, false, PX> c, c2;
+    c.smem = c2.smem = reinterpret_cast<Cx<R>*>(smem_raw);
+    const int tid = threadIdx.x;
+    c.i = tid % S::TL; c.l = tid / S::TL;      // along the axis (global reads of pass 0)
+    c2.i = tid / L; c2.l = tid % L;            // across the lanes (global writes of the last pass)
+    const long long g = tile * L + c.l, g2 = tile * L + c2.l;
+    c.valid = g < a.nlanes; c2.valid = g2 < a.nlanes;
+    const LaneBase lb = lane_base(a, g, c.valid, 0), lb2 = lane_base(a, g2, c2.valid, 0);
+    const R sc = (R)a.scale;
+    SfftGLoad<R, false> gl;
+    gl.in = reinterpret_cast<const Cx<R>*>(a.in) + lb.bi; gl.is_axis = a.is_axis; gl.sgn = a.conj_in ? (R)-1 : (R)1; gl.valid = c.valid;
+    SfftGStore<R, 0> gs;
+    gs.out = reinterpret_cast<Cx<R>*>(a.out) + lb2.bo; gs.os_axis = a.os_axis; gs.sc = sc; gs.sy = a.conj_out ? -sc : sc; gs.valid = c2.valid;
+    gs.fs = nullptr; gs.j2 = 0;
+    Cx<R> v[S::E];
+    sfft_trans_passes<R, S, L, 0>(c, c2, v, reinterpret_cast<const Cx<R>*>(a.tw), gl, gs);
+}
+
 NDFB_DEV unsigned sync_ld_acquire(const unsigned* p) {
 #ifdef NDFB_EMU
     return *p;
@@ -436,6 +486,9 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
             }
             return;
         }
+    }
+    if constexpr (!COLS && S::NP > 1 && L > 1) {
+        if (a.trans_store) { sfft_body_trans<R, S, L>(a, blockIdx.x); return; }
     }
     const long long g = (long long)blockIdx.x * L + c.l;
     c.valid = g < a.nlanes;

@@ -51,7 +51,7 @@ class SlabR2cFft3d:
     """
 
     def __init__(self, shape, dtype=np.float64, group=None, device=None, backend=None, chunks=1, peer="auto",
-                 row_chunks=1, scatter_smem=None, blocked=False, overlap=True):
+                 row_chunks=1, scatter_smem=None, blocked=False, overlap=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -82,6 +82,11 @@ class SlabR2cFft3d:
         self.mp = -(-self.m // lanes128) * lanes128
         self.a_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
         self.b_pad = torch.zeros((self.s0, self.n1, self.mp), dtype=self.ct, device=self.device)
+        if P == 1:
+            # one GPU: keep the intermediate between the axis-1 and axis-0 passes as memory [i1][i0][i2], so that the rows the
+            # last pass READS are 4 KiB apart instead of one 2 MiB page each (the axis-1 pass writes the far-apart rows instead;
+            # 512^3: 0.824 -> 0.797 ms for the two passes, tools/exp_c3_perm.py)
+            self.b_pad = torch.zeros((self.n1, self.s0, self.mp), dtype=self.ct, device=self.device).permute(1, 0, 2)
         self.a = self.a_pad[:, :, :self.m]
         self.b = self.b_pad[:, :, :self.m]
         # result storage for forward(x) without an explicit `out`: padded the same way (the caller gets the [:, :, :m] view),
@@ -262,6 +267,25 @@ class SlabR2cFft3d:
             # chunk q of recv holds rows q*s0:(q+1)*s0 -> already the (n0, s1, mc) axis-1 slab
             be.ndfft(self.recv[c].view(n0, s1, hi - lo), out[:, :, lo:hi], self.h0, 0)
         return out
+
+    def forward_host(self, x_host, out_host, stream=None):
+        """Host-array form of `forward` for this rank's slab: pageable numpy memory -> device through the library's pinned
+        staging ring and copy threads (ndfb_memcpy), the distributed transform, device -> pageable numpy memory.
+        x_host: (n0/P, n1, n2) real C-ordered; out_host: (n0, n1/P, m) complex C-ordered."""
+        import ctypes
+        t, be = self.torch, self.be
+        assert x_host.flags.c_contiguous and out_host.flags.c_contiguous
+        assert tuple(x_host.shape) == (self.s0, self.n1, self.n2) and tuple(out_host.shape) == (self.n0, self.s1, self.m)
+        if getattr(self, "_xdev", None) is None:
+            self._xdev = t.empty((self.s0, self.n1, self.n2), dtype=self.rt, device=self.device)
+            self._odev = t.empty((self.n0, self.s1, self.m), dtype=self.ct, device=self.device)
+        dev = self.device.index if getattr(self.device, "type", "cpu") == "cuda" else 0
+        st = t.cuda.current_stream(self.device).cuda_stream if getattr(self.device, "type", "cpu") == "cuda" else 0
+        dll = be.lib.dll
+        be.lib.check(dll.ndfb_memcpy(ctypes.c_void_p(self._xdev.data_ptr()), ctypes.c_void_p(x_host.ctypes.data), x_host.nbytes, 0, dev or 0, ctypes.c_void_p(st)))
+        self.forward(self._xdev, self._odev)
+        be.lib.check(dll.ndfb_memcpy(ctypes.c_void_p(out_host.ctypes.data), ctypes.c_void_p(self._odev.data_ptr()), out_host.nbytes, 1, dev or 0, ctypes.c_void_p(st)))
+        return out_host
 
     def inverse(self, X, out=None):
         """X: (n0, n1/P, m) complex -> (n0/P, n1, n2) real (Normalization::Default: exact inverse of `forward`)."""

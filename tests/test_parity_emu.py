@@ -589,3 +589,21 @@ def test_schedule_selection_for_the_baseline_shapes(hs, capfd):
         assert "four-step N=8192 = 64 x 128 (strided lanes)" in e and "fs2" not in e, e
     finally:
         del os.environ["NDFB_TRACE"]
+
+
+def test_three_pass_transposing_last_pass(hs, capfd):
+    """Last pass of a three-pass split as the transposing rows kernel (contiguous rows in, lane-interleaved out):
+    64^3 = 64 x (64 x 64) with the 'chip' shrunk by NDFB_FS_CAP; both precisions; and the capped column tile as fallback."""
+    import os
+    os.environ.update({"NDFB_FORCE_FOUR_STEP": "1", "NDFB_FS_CAP": "256", "NDFB_FS_N1": "64", "NDFB_TRACE": "1"})
+    try:
+        hs.run("ndfft", 64 ** 3, (2, 64 ** 3), 1, np.float32, seed=1)
+        hs.run("ndifft", 64 ** 3, (1, 64 ** 3), 1, np.float64, seed=2)
+        err = capfd.readouterr().err
+        assert err.count("rows->lanes (transposing)") == 2, err
+        os.environ["NDFB_NO_TRANS_STORE"] = "1"
+        hs.run("ndfft", 64 ** 3, (1, 64 ** 3), 1, np.float32, seed=3)
+        assert "transposing" not in capfd.readouterr().err
+    finally:
+        for k in ("NDFB_FORCE_FOUR_STEP", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_TRACE", "NDFB_NO_TRANS_STORE"):
+            os.environ.pop(k, None)
