@@ -2,7 +2,7 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 CSRC      := ndrustfft_b200/csrc
-SRCS      := $(CSRC)/ndfft_b200.cu $(sort $(wildcard $(CSRC)/sfft_inst_*.cu) $(wildcard $(CSRC)/rsfft_inst_*.cu) $(wildcard $(CSRC)/bsfft_inst_*.cu) $(wildcard $(CSRC)/fs2_inst*.cu))
+SRCS      := $(CSRC)/ndfft_b200.cu $(sort $(wildcard $(CSRC)/sfft_inst_*.cu) $(wildcard $(CSRC)/rsfft_inst_*.cu) $(wildcard $(CSRC)/bsfft_inst_*.cu) $(wildcard $(CSRC)/fs2_inst*.cu) $(wildcard $(CSRC)/sfft_inst_bulk*.cu))
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh $(CSRC)/*.inc) include/ndfft_b200.h
 # the generated instantiation files only see the kernel headers: host-side edits do not rebuild ~900 kernel instances
 KHDRS     := $(CSRC)/common.h $(CSRC)/devapi.h $(CSRC)/butterflies.cuh $(CSRC)/sfft_kernel.cuh $(CSRC)/sfft_inst.h $(CSRC)/rsfft_tables.inc include/ndfft_b200.h

@@ -551,6 +551,12 @@ static const BsfftEntry* find_bsfft(bool f64, int M, bool cols, long long nlanes
     return best;
 }
 
+// NDFB_ROWS_BULK=1 selects the persistent bulk-async row kernels (A/B against the register-resident ones; default below)
+static int rows_bulk_enabled() {   // 0 off, 1 on for batches that fill the GPU, 2 forced (tests)
+    const char* e = std::getenv("NDFB_ROWS_BULK");
+    return e ? atoi(e) : 0;
+}
+
 // C2C launch: the instantiated Stockham schedule when there is one, else the general tile kernel
 template <typename R>
 static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
@@ -576,6 +582,35 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         const SfftEntry* e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>), s.max_L);
         if (!e && s.max_L) e = find_sfft(sizeof(R) == 8, t.N, cols, nlanes, std::max(llabs_(s.is_axis), llabs_(s.os_axis)) * (long long)sizeof(Cx<R>));
         if (!e && nlanes > 0) e = jit_entry<SfftEntry>(sizeof(R) == 8, -1, t.N, cols, nlanes);
+        // contiguous rows: the persistent bulk-async (TMA + mbarrier) kernel when there is one for this length
+        if (!cols && s.is_axis == 1 && s.os_axis == 1 && !s.fs_twiddle && !s.os_blk && !s.nblk_ptr && rows_bulk_enabled()) {
+            const SfftBulkEntry* be = nullptr;
+            for (int i = 0; i < kSfftBulk_count; ++i)
+                if (kSfftBulk[i].f64 == (sizeof(R) == 8 ? 1 : 0) && kSfftBulk[i].N == t.N) be = &kSfftBulk[i];
+            bool ok = be && (nlanes >= 2LL * be->L * dev_sm_count(p->device) || rows_bulk_enabled() >= 2) && ((uintptr_t)s.in % 16) == 0 &&
+                      ((uintptr_t)s.out % 16) == 0;
+            if (ok && sizeof(R) == 4)
+                for (auto& d : s.dims) if ((d.is % 2) || (d.os % 2)) ok = false;    // every row starts on a 16-byte boundary
+            if (ok) {
+                SfftArgs a;
+                std::memset(&a, 0, sizeof a);
+                a.in = s.in; a.out = s.out; a.nlanes = nlanes; a.nbd = (int)s.dims.size();
+                for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
+                a.is_axis = 1; a.os_axis = 1; a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
+                SfftEntry proxy;
+                std::memset(&proxy, 0, sizeof proxy);
+                for (int i = 0; i < 4; ++i) proxy.r[i] = be->r[i];
+                proxy.twtotal = be->twtotal;
+                void* twd = nullptr;
+                int rc = get_sfft_twiddles<R>(p, s.core, &proxy, &twd);
+                if (rc) return rc;
+                a.tw = twd;
+                const long long ntiles = (nlanes + be->L - 1) / be->L;
+                const long long grid = std::min<long long>(ntiles, (long long)dev_sm_count(p->device) * be->minb);
+                if (std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] sfft %s N=%d rows bulk-async persistent L=%d T=%d smem=%zu tiles=%lld grid=%lld\n", sizeof(R) == 8 ? "f64" : "f32", be->N, be->L, be->threads, be->smem, ntiles, grid);
+                return be->launch(a, (unsigned)grid, stream);
+            }
+        }
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
             if (trace) fprintf(stderr, "[ndfb] sfft %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c%s radix=%d.%d.%d.%d\n", sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A', e->jit_func ? " jit" : "", e->r[0], e->r[1], e->r[2], e->r[3]);

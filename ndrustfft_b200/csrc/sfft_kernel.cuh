@@ -434,6 +434,137 @@ NDFB_DEV void sfft_body_trans(const SfftArgs& a, long long tile) {
     sfft_trans_passes<R, S, L, 0>(c, c2, v, reinterpret_cast<const Cx<R>*>(a.tw), gl, gs);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Contiguous rows as a PERSISTENT, bulk-async pipelined kernel (TMA 1-D copies + mbarrier):
+//     TMA load of tile t+1 -> [in buffer]      |  passes of tile t on [work buffer]  |   TMA store of tile t-1 <- [out buffer]
+// One elected thread issues cp.async.bulk global->shared with an mbarrier transaction count; every thread waits on the
+// barrier's phase; pass 0 reads its points from the in buffer (LDS instead of LDG: no global latency on the critical
+// path), the buffer is handed back to the TMA engine right after pass 0, the last pass writes natural order into the
+// out buffer and one thread sends it with cp.async.bulk shared->global.  The register-resident row kernel needs two CTAs
+// per SM to cover its own load / store phases; here the copy engine covers them and the SM only issues FFT work.
+// ------------------------------------------------------------------------------------------------------
+#ifdef NDFB_EMU
+struct BulkBar { unsigned long long v; };
+NDFB_DEV void bulk_bar_init(BulkBar* b) { b->v = 0; }
+NDFB_DEV void bulk_load_issue(void* sdst, const void* gsrc, unsigned bytes, BulkBar*) {
+    unsigned char* d = reinterpret_cast<unsigned char*>(sdst);
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(gsrc);
+    for (unsigned i = 0; i < bytes; ++i) d[i] = q[i];
+}
+NDFB_DEV void bulk_bar_expect(BulkBar*, unsigned) {}
+NDFB_DEV void bulk_bar_wait(BulkBar*, unsigned) {}
+NDFB_DEV void bulk_store_wait_read() {}
+#else
+struct BulkBar { unsigned long long v; };
+NDFB_DEV void bulk_bar_init(BulkBar* b) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the init must be visible to the async proxy
+}
+NDFB_DEV void bulk_bar_expect(BulkBar* b, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+NDFB_DEV void bulk_load_issue(void* sdst, const void* gsrc, unsigned bytes, BulkBar* b) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(sdst), a = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
+}
+NDFB_DEV void bulk_bar_wait(BulkBar* b, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+NDFB_DEV void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+
+template <typename R, class S, int L>
+struct SfftBulkSmem {
+    static constexpr size_t kWork = sizeof(Cx<R>) * (size_t)L * S::NPAD;
+    static constexpr size_t kIO = sizeof(Cx<R>) * (size_t)L * S::N;
+    static constexpr size_t kTotal = kWork + 2 * kIO + 16;
+};
+
+template <typename R, class S, int L, int MINB>
+__global__ void __launch_bounds__(S::TL* L, MINB) sfft_rows_bulk_kernel(const __grid_constant__ SfftArgs a) {
+    static_assert(S::NP > 1, "single-pass schedules have nothing to overlap");
+    NDFB_DYN_SMEM(smem_raw);
+    using SM = SfftBulkSmem<R, S, L>;
+    Cx<R>* work = reinterpret_cast<Cx<R>*>(smem_raw);
+    Cx<R>* inb = reinterpret_cast<Cx<R>*>(smem_raw + SM::kWork);
+    Cx<R>* outb = reinterpret_cast<Cx<R>*>(smem_raw + SM::kWork + SM::kIO);
+    BulkBar* bar = reinterpret_cast<BulkBar*>(smem_raw + SM::kWork + 2 * SM::kIO);
+    SfftCtx<R, S, L, false> c;
+    c.smem = work;
+    const int tid = threadIdx.x;
+    c.i = tid % S::TL; c.l = tid / S::TL;
+    const long long ntiles = (a.nlanes + L - 1) / L;
+    constexpr unsigned kRowBytes = (unsigned)(sizeof(Cx<R>) * S::N);
+    const Cx<R>* __restrict__ tw = reinterpret_cast<const Cx<R>*>(a.tw);
+    const R sc = (R)a.scale;
+    const R sy = a.conj_out ? -sc : sc;
+    const R sgn_in = a.conj_in ? (R)-1 : (R)1;
+    // one thread: bring the rows of `tile` into the in buffer (one bulk copy per lane: lanes need not be adjacent in memory)
+    auto issue_load = [&](long long tile) {
+        unsigned total = 0;
+        for (int l = 0; l < L; ++l)
+            if (tile * L + l < a.nlanes) total += kRowBytes;
+        bulk_bar_expect(bar, total);
+        for (int l = 0; l < L; ++l) {
+            const long long g = tile * L + l;
+            if (g >= a.nlanes) break;
+            const LaneBase lb = lane_base(a, g, true, 0);
+            bulk_load_issue(inb + (size_t)l * S::N, reinterpret_cast<const Cx<R>*>(a.in) + lb.bi, kRowBytes, bar);
+        }
+    };
+    if (tid == 0) {
+        bulk_bar_init(bar);
+        if ((long long)blockIdx.x < ntiles) issue_load(blockIdx.x);
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    Cx<R> v[S::E];
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tid == 0) bulk_store_wait_read();      // the previous tile's store has finished READING the out buffer
+        bulk_bar_wait(bar, parity);                 // this tile's rows have landed in the in buffer
+        parity ^= 1u;
+        const bool valid = tile * L + c.l < a.nlanes;
+        const Cx<R>* __restrict__ row = inb + (size_t)c.l * S::N;
+        auto load = [&](int j) -> Cx<R> {
+            Cx<R> x = valid ? row[j] : cmake<R>((R)0, (R)0);
+            x.y *= sgn_in;
+            return x;
+        };
+        Cx<R>* __restrict__ orow = outb + (size_t)c.l * S::N;
+        auto store = [&](int k, Cx<R> val) { orow[k] = cmake<R>(val.x * sc, val.y * sy); };
+        SfftPass<R, S, L, false, 0, false, false>::run(c, v, tw, load, store);    // ends with a barrier: the in buffer is free
+        if (tid == 0 && tile + gridDim.x < ntiles) issue_load(tile + gridDim.x);  // next tile streams in behind the passes
+        SfftAll<R, S, L, false, 1, false, false>::run(c, v, tw, load, store);
+        bulk_store_fence();
+        __syncthreads();
+        if (tid == 0) {
+            for (int l = 0; l < L; ++l) {
+                const long long g = tile * L + l;
+                if (g >= a.nlanes) break;
+                const LaneBase lb = lane_base(a, g, true, 0);
+                bulk_store_issue(reinterpret_cast<Cx<R>*>(a.out) + lb.bo, outb + (size_t)l * S::N, kRowBytes);
+            }
+#ifndef NDFB_EMU
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+        }
+    }
+    if (tid == 0) bulk_store_wait_read();
+}
+
 NDFB_DEV unsigned sync_ld_acquire(const unsigned* p) {
 #ifdef NDFB_EMU
     return *p;

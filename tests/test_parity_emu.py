@@ -607,3 +607,18 @@ def test_three_pass_transposing_last_pass(hs, capfd):
     finally:
         for k in ("NDFB_FORCE_FOUR_STEP", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_TRACE", "NDFB_NO_TRANS_STORE"):
             os.environ.pop(k, None)
+
+
+def test_rows_bulk_async_kernel(hs, capfd):
+    """Persistent bulk-async row kernel (TMA loads / stores + mbarrier on the GPU; plain copies under the emulator):
+    several tiles per CTA, a ragged last tile, forward and inverse, both precisions."""
+    import os
+    os.environ.update({"NDFB_ROWS_BULK": "2", "NDFB_TRACE": "1"})
+    try:
+        hs.run("ndfft", 1024, (11, 1024), 1, np.float32, seed=1)            # L = 4: 3 tiles, the last one ragged
+        hs.run("ndifft", 512, (9, 512), 1, np.float64, seed=2)
+        hs.run("ndfft", 512, (3, 5, 512), 2, np.float64, seed=3, norm="none")
+        err = capfd.readouterr().err
+        assert err.count("rows bulk-async persistent") == 3, err
+    finally:
+        os.environ.pop("NDFB_ROWS_BULK", None); os.environ.pop("NDFB_TRACE", None)

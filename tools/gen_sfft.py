@@ -238,6 +238,25 @@ def fs2_entries():
     return out
 
 
+def bulk_entries():
+    """Persistent bulk-async row kernels (sfft_rows_bulk_kernel): family-B schedules for the long power-of-two rows."""
+    out = []
+    for f64, lengths in ((0, (1024, 2048, 4096, 8192)), (1, (512, 1024, 2048, 4096))):
+        cs = 16 if f64 else 8
+        R = "double" if f64 else "float"
+        for N in lengths:
+            TL, rad = pow2_schedule(N, f64, 1)
+            rad = rad + [1] * (4 - len(rad))
+            L = rows_L(N, TL, rad[0], cs)
+            while L > 1 and L * (npad(N, rad[0]) + 2 * N) * cs + 16 > 110 * 1024:
+                L //= 2
+            smem = L * (npad(N, rad[0]) + 2 * N) * cs + 16
+            T = TL * L
+            minb = max(1, min((227 * 1024) // smem, 65536 // (T * 64), 4))
+            out.append(f"    SFFT_BULK_ENTRY({R}, {f64}, {N}, {TL}, {rad[0]}, {rad[1]}, {rad[2]}, {rad[3]}, {L}, {minb}),  // T={T} smem={smem}")
+    return out
+
+
 def dedup(entries):
     seen, out = set(), []
     for e in entries:
@@ -278,6 +297,9 @@ def main():
         write(f"bsfft_inst_{nm}.cu", head + [f"const BsfftEntry kBsfft_{nm}[] = {{"] + [fmt(e, "BSFFT_ENTRY") for e in ents] +
               ["};", f"const int kBsfft_{nm}_count = {len(ents)};", "", "}  // namespace ndfb"])
         total += len(ents)
+    ents = bulk_entries()
+    write("sfft_inst_bulk.cu", head + ["const SfftBulkEntry kSfftBulk[] = {"] + ents + ["};", f"const int kSfftBulk_count = {len(ents)};", "", "}  // namespace ndfb"])
+    total += len(ents)
     ents = fs2_entries()
     write("fs2_inst.cu", head + ["const Fs2Entry kFs2[] = {"] + ents + ["};", f"const int kFs2_count = {len(ents)};", "", "}  // namespace ndfb"])
     total += len(ents)
