@@ -43,6 +43,8 @@ struct SfftArgs {
     long long wait_group;
     unsigned wait_need;
     long long ntiles;      // persistent launches: total number of tiles (0 = one tile per CTA)
+    long long l2_prefetch_lanes;   // != 0 (contiguous rows): lane distance of the row this CTA asks the L2 to fetch ahead (one
+                                   // cp.async.bulk.prefetch.L2 per row: the CTA that later owns it finds it at L2 latency)
     int trans_store;       // != 0 (row kernels): the tile's lanes are far apart in the input but ADJACENT in the output (last pass of a
                            // three-pass split): rows are read along the axis, the last pass re-maps threads so that stores run across lanes
     int bulk_store;        // != 0 (with nblk_ptr): the tile's block for each destination is one contiguous range there: stage the result
@@ -621,6 +623,18 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     if constexpr (!COLS && S::NP > 1 && L > 1) {
         if (a.trans_store) { sfft_body_trans<R, S, L>(a, blockIdx.x); return; }
     }
+#ifndef NDFB_EMU
+    if constexpr (!COLS) {
+        if (a.l2_prefetch_lanes && tid < L) {
+            const long long gp = (long long)blockIdx.x * L + tid + a.l2_prefetch_lanes;
+            if (gp < a.nlanes) {
+                const LaneBase lp = lane_base(a, gp, true, 0);
+                const Cx<R>* row = reinterpret_cast<const Cx<R>*>(a.in) + lp.bi;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((unsigned)(sizeof(Cx<R>) * S::N)) : "memory");
+            }
+        }
+    }
+#endif
     const long long g = (long long)blockIdx.x * L + c.l;
     c.valid = g < a.nlanes;
     const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
