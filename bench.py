@@ -455,7 +455,7 @@ def c2_step_bench(nb, torch, np, dev, local, steps, warmup):
 
 
 # per-launch DRAM traffic of the dominant kernel from one `ncu --set full` capture of this command (profiles/)
-C3_TRAFFIC = {"bytes": 2.156e9, "source": "ncu --set full, profiles/r2e_ncu_c3_summary.txt: sfft_kernel<double, Sched<512,64,8,8,8>, cols> dram__bytes_read 1.116 GB + "
+C3_TRAFFIC = {"bytes": 2.156e9, "source": "ncu --set full, profiles/round2/r2e_ncu_c3_summary.txt: sfft_kernel<double, Sched<512,64,8,8,8>, cols> dram__bytes_read 1.116 GB + "
                                               "dram__bytes_write 1.039 GB per launch = 1.00 x the algorithmic 2.156 GB; the r2c kernel: 1.107 + 1.027 GB for 2.152 GB"}
 
 
@@ -514,7 +514,7 @@ def main():
 
     # ---- the headline transform ----
     # i2-chunked overlap of the exchange with the last pass loses at every N measured (8 GPUs, CUDA graph: 0.295 ms unchunked,
-    # 0.315 / 0.341 / 0.383 ms with 2 / 4 / 8 chunks; profiles/r2b_c3_probe_n8.jsonl), so the default pipeline is unchunked
+    # 0.315 / 0.341 / 0.383 ms with 2 / 4 / 8 chunks; profiles/round2/r2b_c3_probe_n8.jsonl), so the default pipeline is unchunked
     chunks = args.chunks or 1
     plan = SlabR2cFft3d((N3, N3, N3), np.float64, device=dev, chunks=chunks)
     s0, s1 = N3 // world, N3 // world

@@ -508,7 +508,7 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     for (int i = 0; i < 8; ++i) a.blk_ptr[i] = s.blk_ptr[i];
     a.trans_store = trans_next ? 1 : 0;
     // long contiguous rows: every CTA asks the L2 for the row that will be started when it retires (NDFB_L2_PREFETCH=<waves>, 0 = off)
-    // Measured on B200 (tools/ab_l2_prefetch.py, profiles/r2k_ab_l2_prefetch.jsonl): half a wave ahead gains 2-4 % on 32-64 KiB
+    // Measured on B200 (tools/ab_l2_prefetch.py, profiles/round2/r2k_ab_l2_prefetch.jsonl): half a wave ahead gains 2-4 % on 32-64 KiB
     // rows (8192-point c64: 0.255 -> 0.245 ms), one or two waves ahead lose (the lines are evicted or fight the demand loads).
     if (!e->cols && s.is_axis == 1 && !trans_next && (size_t)e->N * sizeof(Cx<R>) >= 32768 && ((uintptr_t)s.in % 16) == 0) {
         static const double waves = std::getenv("NDFB_L2_PREFETCH") ? atof(std::getenv("NDFB_L2_PREFETCH")) : 0.5;
