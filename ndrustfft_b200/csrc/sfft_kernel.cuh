@@ -248,6 +248,26 @@ struct SfftAll {
     }
 };
 
+// passes PASS .. STOP-1 only (none of them the last one): callers that give the last pass a mapping of their own
+template <typename R, class S, int L, bool COLS, int PASS, int STOP, bool SYNC0>
+struct SfftUntil {
+    template <class Ctx, typename LoadF, typename StoreF>
+    static NDFB_DEV void run(const Ctx& c, Cx<R> (&v)[S::E], const Cx<R>* tw, LoadF load, StoreF store) {
+        if constexpr (PASS < STOP) {
+            SfftPass<R, S, L, COLS, PASS, SYNC0, false>::run(c, v, tw, load, store);
+            SfftUntil<R, S, L, COLS, PASS + 1, STOP, SYNC0>::run(c, v, tw, load, store);
+        }
+    }
+};
+
+// Mirror-paired last pass for the real kinds whose outputs need Z[k] AND Z[N-k] (R2C, DCT-I, DCT-II): when the last pass has
+// two butterflies per thread, thread i takes butterflies i and NB - i (thread 0: 0 and NB/2), whose outputs are exactly each
+// other's mirror bins (k = b + q NB  <->  N - k = (NB - b) + (r-1-q) NB).  The pair epilogue then runs from registers: no
+// write of the spectrum to shared memory, no barrier, no read-back — one shared-memory round trip less per lane.
+template <class S>
+constexpr bool kMirrorEpi = S::NP >= 2 && S::G(S::NP - 1) == 2 && S::nbf(S::NP - 1) == 2 * S::TL && S::nbf(S::NP - 1) % 2 == 0 &&
+                            S::radix(S::NP - 1) % 2 == 0;
+
 // lane -> global base offsets (elements of the respective array); also the index along the fastest batch dim
 struct LaneBase {
     long long bi, bo;
@@ -1012,6 +1032,67 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     };
 
     Cx<R> v[S::E];
+    if constexpr (PAIR_EPI && kMirrorEpi<S>) {
+        constexpr int LP = S::NP - 1, r = S::radix(LP), P = S::before(LP), NB = S::nbf(LP);
+        SfftUntil<R, S, L, COLS, 0, LP, STAGE_IN || PAIR_PRO>::run(c, v, tw, load, store);
+        const int i = c.i;
+        const int b0 = i, b1 = i == 0 ? NB / 2 : NB - i;
+#pragma unroll
+        for (int q = 0; q < r; ++q) {
+            v[q] = c.smem[c.addr(b0 + q * NB)];
+            v[r + q] = c.smem[c.addr(b1 + q * NB)];
+        }
+        {
+            const Cx<R>* __restrict__ t0 = tw + S::twoff(LP) + (b0 % P);
+            const Cx<R>* __restrict__ t1 = tw + S::twoff(LP) + (b1 % P);
+#pragma unroll
+            for (int q = 1; q < r; ++q) {
+                v[q] = cmul(v[q], ldg(&t0[(q - 1) * P]));
+                v[r + q] = cmul(v[r + q], ldg(&t1[(q - 1) * P]));
+            }
+        }
+        Dft<R, r>::run(&v[0]);
+        Dft<R, r>::run(&v[r]);
+        // bins k and k2 = N - k of the length-2N real DFT from Z[k] = zk and Z[N-k] = zm (k = 0: zm = Z[0], k2 = N)
+        auto emit = [&](int k, Cx<R> zk, Cx<R> zm) {
+            const int k2 = N - k;
+            const Cx<R> zc = cconj(zm);
+            const Cx<R> w = ldg(&tabA[k]);
+            const Cx<R> s = cadd(zk, zc), d = cmul(w, csub(zk, zc));
+            const Cx<R> X = cmake<R>((R)0.5 * (s.x + d.y), (R)0.5 * (s.y - d.x));
+            const Cx<R> X2 = cmake<R>((R)0.5 * (s.x - d.y), (R)-0.5 * (s.y + d.x));
+            if (!valid) return;
+            const bool two = k2 != k;
+            if (KIND == RK_R2C) {
+                out_c[(long long)k * os_axis] = cmake<R>(sc * X.x, sc * X.y);
+                if (two) out_c[(long long)k2 * os_axis] = cmake<R>(sc * X2.x, sc * X2.y);
+            } else if (KIND == RK_DCT1) {
+                out_r[(long long)k * os_axis] = (R)0.5 * sc * X.x;
+                if (two) out_r[(long long)k2 * os_axis] = (R)0.5 * sc * X2.x;
+            } else {  // RK_DCT2
+                const Cx<R> A = cmul(X, ldg(&tabB[k]));
+                out_r[(long long)k * os_axis] = sc * A.x;
+                if (k > 0 && k < N) out_r[(long long)(n - k) * os_axis] = -sc * A.y;
+                if (two) {
+                    const Cx<R> A2 = cmul(X2, ldg(&tabB[k2]));
+                    out_r[(long long)k2 * os_axis] = sc * A2.x;
+                    if (k2 > 0 && k2 < N) out_r[(long long)(n - k2) * os_axis] = -sc * A2.y;
+                }
+            }
+        };
+        if (i != 0) {
+#pragma unroll
+            for (int q = 0; q < r; ++q) emit(b0 + q * NB, v[q], v[r + (r - 1 - q)]);
+        } else {
+            emit(0, v[0], v[0]);                                        // bins 0 and N, both from Z[0]
+#pragma unroll
+            for (int q = 1; q < r / 2; ++q) emit(q * NB, v[q], v[r - q]);
+            emit((r / 2) * NB, v[r / 2], v[r / 2]);                     // k = N/2 pairs with itself
+#pragma unroll
+            for (int q = 0; q < r / 2; ++q) emit(NB / 2 + q * NB, v[r + q], v[r + (r - 1 - q)]);
+        }
+        return;
+    }
     SfftAll<R, S, L, COLS, 0, STAGE_IN || PAIR_PRO, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
 
     if (PAIR_EPI) {

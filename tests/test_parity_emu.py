@@ -622,3 +622,13 @@ def test_rows_bulk_async_kernel(hs, capfd):
         assert err.count("rows bulk-async persistent") == 3, err
     finally:
         os.environ.pop("NDFB_ROWS_BULK", None); os.environ.pop("NDFB_TRACE", None)
+
+
+@pytest.mark.parametrize("op,n,rd", [("ndfft_r2c", 512, np.float64), ("nddct2", 4096, np.float64), ("nddct1", 2049, np.float64),
+                                     ("ndfft_r2c", 4096, np.float32), ("nddct2", 512, np.float64), ("nddct2", 4096, np.float32)])
+def test_mirror_paired_last_pass(hs, op, n, rd):
+    """Schedules whose last pass has two butterflies per thread run the pair epilogue from registers (thread i owns
+    butterflies i and NB - i: bins k and N - k): 256-point f64 core (8.8.4: c3's r2c), 2048-point f64 core (8.8.8.4: c4's
+    DCT-II / DCT-I of 2049), 2048-point f32 core (16.16.8); rows and columns, ragged tiles."""
+    hs.run(op, n, (3, n), 1, rd, seed=n)
+    hs.run(op, n, (n, 5), 0, rd, seed=n + 1, norm="none")
