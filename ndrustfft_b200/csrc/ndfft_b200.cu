@@ -1402,7 +1402,7 @@ struct HostArray {
     const void* user = nullptr;          // caller's pointer (element [0, 0, ...])
     void* base = nullptr;                // pointer the device path is handed for element [0, 0, ...] (user or packed)
     std::vector<ptrdiff_t> strides;      // strides matching `base`
-    std::vector<char> packed;            // owns the dense copy when the view has gaps
+    std::unique_ptr<char[]> packed;      // owns the dense copy when the view has gaps (uninitialised: every element is written)
     bool is_packed = false;
     long long lo = 0, hi = 0;            // byte span relative to base
     void init(const void* ptr, int ndim, const size_t* shape, const ptrdiff_t* st, size_t elem, bool gather) {
@@ -1413,14 +1413,14 @@ struct HostArray {
         is_packed = true;
         size_t total = elem;
         for (int d = 0; d < ndim; ++d) total *= shape[d];
-        packed.resize(total);
+        packed.reset(new char[total ? total : 1]);
         strides = c_strides_of(ndim, shape);
-        base = packed.data();
+        base = packed.get();
         lo = 0; hi = (long long)total;
-        if (gather) host_nd_copy(true, packed.data(), const_cast<void*>(ptr), ndim, shape, st, elem);
+        if (gather) host_nd_copy(true, packed.get(), const_cast<void*>(ptr), ndim, shape, st, elem);
     }
     void scatter_back(int ndim, const size_t* shape, const ptrdiff_t* user_strides, size_t elem) {
-        if (is_packed) host_nd_copy(false, packed.data(), const_cast<void*>(user), ndim, shape, user_strides, elem);
+        if (is_packed) host_nd_copy(false, packed.get(), const_cast<void*>(user), ndim, shape, user_strides, elem);
     }
 };
 
@@ -1482,16 +1482,16 @@ static int exec_host_pipelined(ndfb_plan* p, const OpInfo& o, double extra_scale
         const size_t iw = (hi - lo) * (size_t)strides_in[d] * ie, ow = (hi - lo) * (size_t)strides_out[d] * oe;
         const size_t irows = d == 0 ? 1 : shape_in[0], orows = d == 0 ? 1 : shape_out[0];
         const size_t ipitch = d == 0 ? iw : (size_t)strides_in[0] * ie, opitch = d == 0 ? ow : (size_t)strides_out[0] * oe;
-        if ((rc = ring.h2d((char*)din + ioff, ipitch, (const char*)in + ioff, ipitch, iw, irows, in_pageable, g_pipe.s[0]))) { cudaDeviceSynchronize(); return rc; }
+        if ((rc = ring.h2d((char*)din + ioff, ipitch, (const char*)in + ioff, ipitch, iw, irows, in_pageable, g_pipe.s[0]))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
         NDFB_CUDA(cudaEventRecord(g_pipe.ev_in[c], g_pipe.s[0]));
         NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ev_in[c], 0));
         rc = exec_device<R>(p, o, extra_scale, (const char*)din + ioff, (char*)dout + ooff, ndim, shi.data(), strides_in, sho.data(),
                             strides_out, axis, g_pipe.s[1]);
-        if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (rc) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
         NDFB_CUDA(cudaEventRecord(g_pipe.ev_k[c], g_pipe.s[1]));
         NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[2], g_pipe.ev_k[c], 0));
-        if ((rc = ring.d2h((char*)out + ooff, opitch, (const char*)dout + ooff, opitch, ow, orows, out_pageable, g_pipe.s[2]))) { cudaDeviceSynchronize(); return rc; }
-        if ((rc = ring.drain(false))) { cudaDeviceSynchronize(); return rc; }
+        if ((rc = ring.d2h((char*)out + ooff, opitch, (const char*)dout + ooff, opitch, ow, orows, out_pageable, g_pipe.s[2]))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
+        if ((rc = ring.drain(false))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
     }
     if ((rc = ring.drain(true))) return rc;
     NDFB_CUDA(cudaStreamSynchronize(g_pipe.s[2]));
@@ -1653,18 +1653,18 @@ static int chain_host_pipelined(const std::vector<ChainStep>& st, const void* hi
             const size_t lo = nd * c / K0, hi = nd * (c + 1) / K0;
             if (hi == lo) continue;
             const ChunkGeom g = chunk_geom(din, d0, lo, hi, ie);
-            if ((rc = ring.h2d((char*)din.ptr + g.off, g.pitch, (const char*)hin + g.off, g.pitch, g.width, g.rows, in_pageable, g_pipe.s[0]))) { cudaDeviceSynchronize(); return rc; }
+            if ((rc = ring.h2d((char*)din.ptr + g.off, g.pitch, (const char*)hin + g.off, g.pitch, g.width, g.rows, in_pageable, g_pipe.s[0]))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
             NDFB_CUDA(cudaEventRecord(g_pipe.ev_in[c], g_pipe.s[0]));
             NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ev_in[c], 0));
             a.shape[d0] = b.shape[d0] = hi - lo;
             rc = exec_device<R>(p, st[0].o, 1.0, (const char*)din.ptr + g.off, (char*)d1.ptr + lo * (size_t)d1.strides[d0] * e1, ndim,
                                 a.shape.data(), a.strides.data(), b.shape.data(), b.strides.data(), st[0].axis, g_pipe.s[1]);
-            if (rc) { cudaDeviceSynchronize(); return rc; }
+            if (rc) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
         }
     }
     // middle steps on the whole array
     ChainView cur = d1;
-    if (n > 2 && (rc = chain_device<R>(st, din, dout, g_pipe.s[1], 1, n - 2, &cur))) { cudaDeviceSynchronize(); return rc; }
+    if (n > 2 && (rc = chain_device<R>(st, din, dout, g_pipe.s[1], 1, n - 2, &cur))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
     // last step, piece by piece ahead of the download
     {
         const ChainStep& L = st[n - 1];
@@ -1678,11 +1678,11 @@ static int chain_host_pipelined(const std::vector<ChainStep>& st, const void* hi
             a.shape[dl] = b.shape[dl] = hi - lo;
             rc = exec_device<R>(L.p, L.o, 1.0, (const char*)cur.ptr + lo * (size_t)cur.strides[dl] * el, (char*)dout.ptr + g.off, ndim,
                                 a.shape.data(), a.strides.data(), b.shape.data(), b.strides.data(), L.axis, g_pipe.s[1]);
-            if (rc) { cudaDeviceSynchronize(); return rc; }
+            if (rc) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
             NDFB_CUDA(cudaEventRecord(g_pipe.ev_k[c], g_pipe.s[1]));
             NDFB_CUDA(cudaStreamWaitEvent(g_pipe.s[2], g_pipe.ev_k[c], 0));
-            if ((rc = ring.d2h((char*)hout + g.off, g.pitch, (const char*)dout.ptr + g.off, g.pitch, g.width, g.rows, out_pageable, g_pipe.s[2]))) { cudaDeviceSynchronize(); return rc; }
-            if ((rc = ring.drain(false))) { cudaDeviceSynchronize(); return rc; }
+            if ((rc = ring.d2h((char*)hout + g.off, g.pitch, (const char*)dout.ptr + g.off, g.pitch, g.width, g.rows, out_pageable, g_pipe.s[2]))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
+            if ((rc = ring.drain(false))) { cudaDeviceSynchronize(); g_pipe.ring.pend.clear(); return rc; }
         }
     }
     if ((rc = ring.drain(true))) return rc;
