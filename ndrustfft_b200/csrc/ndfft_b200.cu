@@ -255,7 +255,7 @@ static int preferred_family(bool f64, int N, bool cols, bool real_kind) {
 // resident threads per SM this entry can expect (registers estimated from the points per thread)
 template <typename E>
 static int resident_threads(const E* e) {
-    const int regs = e->f64 ? e->E * 4 + (e->fam == 1 ? 32 : 56) : e->E * 2 + (e->fam == 1 ? 32 : 44);
+    const int regs = e->f64 ? e->E * 4 + (e->fam >= 1 ? 32 : 56) : e->E * 2 + (e->fam >= 1 ? 32 : 44);
     int ctas = 65536 / (e->threads * (regs < 32 ? 32 : regs));
     if (e->smem) ctas = std::min<int>(ctas, (int)((227 * 1024) / e->smem));
     ctas = std::max(ctas, e->minb);     // __launch_bounds__ guarantees at least this many (register-capped variants)
@@ -688,12 +688,16 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
                 }
         }
     }
-    const int pref = preferred_family(f64, N, cols, true);
+    // family 2 = family B with the small radix FIRST: only for the kinds whose prologue pairs bins j and N-j (C2R, DCT-III),
+    // where it lets pass 0 run mirror-paired from registers (kMirrorPro); preferred there, ignored elsewhere
+    const bool wants_rev = (rkind == RK_C2R || rkind == RK_DCT3) && !std::getenv("NDFB_NO_MIRROR_PRO");
+    const int pref = wants_rev ? 2 : preferred_family(f64, N, cols, true);
     const RsfftEntry* best = nullptr;
     for (const Tab& t : tabs)
         for (int i = 0; i < t.n; ++i) {
             const RsfftEntry* e = &t.e[i];
             if (e->f64 != (f64 ? 1 : 0) || e->kind != rkind || e->N != N || e->cols != (cols ? 1 : 0)) continue;
+            if (e->fam == 2 && !wants_rev) continue;
             if (better_entry(e, best, nlanes, pref, f64 ? (size_t)8 : (size_t)4, axis_stride_bytes)) best = e;
         }
     return best;
@@ -739,7 +743,7 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
         }
         if (e) {
             const bool trace = std::getenv("NDFB_TRACE") != nullptr;
-            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c%s\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam ? 'B' : 'A', e->jit_func ? " jit" : "");
+            if (trace) fprintf(stderr, "[ndfb] rsfft kind=%d %s N=%d %s L=%d T=%d smem=%zu lanes=%lld minb=%d fam=%c%s\n", rk, sizeof(R) == 8 ? "f64" : "f32", e->N, e->cols ? "cols" : "rows", e->L, e->threads, e->smem, nlanes, e->minb, e->fam == 2 ? 'R' : e->fam ? 'B' : 'A', e->jit_func ? " jit" : "");
             RsfftArgs a;
             std::memset(&a, 0, sizeof a);
             a.in = s.in; a.out = s.out; a.nlanes = nlanes;

@@ -268,6 +268,11 @@ template <class S>
 constexpr bool kMirrorEpi = S::NP >= 2 && S::G(S::NP - 1) == 2 && S::nbf(S::NP - 1) == 2 * S::TL && S::nbf(S::NP - 1) % 2 == 0 &&
                             S::radix(S::NP - 1) % 2 == 0;
 
+// The same pairing on the FIRST pass for the kinds whose inputs come in mirror pairs (C2R, DCT-III: slots j and N-j are built
+// from the same two spectrum bins): schedules that START with the small radix (4.8.8.8) give pass 0 two butterflies per thread.
+template <class S>
+constexpr bool kMirrorPro = S::NP >= 2 && S::G(0) == 2 && S::nbf(0) == 2 * S::TL && S::nbf(0) % 2 == 0 && S::R0 % 2 == 0;
+
 // lane -> global base offsets (elements of the respective array); also the index along the fastest batch dim
 struct LaneBase {
     long long bi, bo;
@@ -933,7 +938,8 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     // because tabA[N-j] = -conj(tabA[j])), so one thread loads them once and writes both slots to the shared buffer;
     // the first pass then reads plain complex slots.  Halves the global/table loads and the prologue arithmetic. ----
     constexpr bool PAIR_PRO = KIND == RK_C2R || KIND == RK_DCT3;
-    if (PAIR_PRO) {
+    constexpr bool MIRROR_PRO = PAIR_PRO && kMirrorPro<S>;
+    if (PAIR_PRO && !MIRROR_PRO) {
         constexpr int ITQ = (N / 2 + 1 + S::TL - 1) / S::TL;
 #pragma unroll
         for (int m = 0; m < ITQ; ++m) {
@@ -1093,7 +1099,54 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
         }
         return;
     }
-    SfftAll<R, S, L, COLS, 0, STAGE_IN || PAIR_PRO, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
+    if constexpr (MIRROR_PRO) {
+        // pass 0 with butterflies i and NB - i in one thread: the zip of bins j and N - j feeds both, straight from global memory
+        constexpr int r = S::R0, NB = S::nbf(0);
+        auto zip = [&](int j, Cx<R>& zj, Cx<R>& zm) {      // z[j] and z[N - j] (j = 0: zm unused; j = N/2: both equal)
+            const int k2 = N - j;
+            Cx<R> xk, xn;
+            if (KIND == RK_C2R) {
+                xk = valid ? in_c[(long long)j * is_axis] : cmake<R>(zero, zero);
+                xn = valid ? in_c[(long long)k2 * is_axis] : cmake<R>(zero, zero);
+                if (j == 0) { xk.y = zero; xn.y = zero; }        // Im X[0], Im X[N] dropped (src/lib.rs:516-521)
+            } else {
+                Cx<R> pk = cmake<R>(gin(j), j == 0 ? zero : -gin(n - j));
+                Cx<R> pn = cmake<R>(gin(k2), -gin(n - k2));
+                xk = cmul(pk, cconj(ldg(&tabB[j])));
+                xn = cmul(pn, cconj(ldg(&tabB[k2])));
+            }
+            const Cx<R> wc = cconj(ldg(&tabA[j]));
+            const Cx<R> E = cadd(xk, cconj(xn)), O = csub(xk, cconj(xn));
+            const Cx<R> iw = cmul_i(cmul(wc, O));
+            zj = cconj(cadd(E, iw));
+            zm = csub(E, iw);
+        };
+        const int i = c.i;
+        const int b0 = i, b1 = i == 0 ? NB / 2 : NB - i;
+        Cx<R> dump;
+        if (i != 0) {
+#pragma unroll
+            for (int q = 0; q < r; ++q) zip(b0 + q * NB, v[q], v[r + (r - 1 - q)]);
+        } else {
+            zip(0, v[0], dump);
+#pragma unroll
+            for (int q = 1; q < r / 2; ++q) zip(q * NB, v[q], v[r - q]);
+            zip((r / 2) * NB, v[r / 2], dump);
+#pragma unroll
+            for (int q = 0; q < r / 2; ++q) zip(NB / 2 + q * NB, v[r + q], v[r + (r - 1 - q)]);
+        }
+        Dft<R, r>::run(&v[0]);
+        Dft<R, r>::run(&v[r]);
+#pragma unroll
+        for (int q = 0; q < r; ++q) {
+            c.smem[c.addr(b0 * r + q)] = v[q];          // pass 0 of the autosort: Y[b r + q]
+            c.smem[c.addr(b1 * r + q)] = v[r + q];
+        }
+        __syncthreads();
+        SfftAll<R, S, L, COLS, 1, false, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
+    } else {
+        SfftAll<R, S, L, COLS, 0, STAGE_IN || PAIR_PRO, (PAIR_EPI || STAGE_OUT) && (S::NP > 1)>::run(c, v, tw, load, store);
+    }
 
     if (PAIR_EPI) {
         __syncthreads();

@@ -632,3 +632,18 @@ def test_mirror_paired_last_pass(hs, op, n, rd):
     DCT-II / DCT-I of 2049), 2048-point f32 core (16.16.8); rows and columns, ragged tiles."""
     hs.run(op, n, (3, n), 1, rd, seed=n)
     hs.run(op, n, (n, 5), 0, rd, seed=n + 1, norm="none")
+
+
+@pytest.mark.parametrize("op,n,rd", [("ndifft_r2c", 512, np.float64), ("nddct3", 4096, np.float64), ("ndifft_r2c", 4096, np.float32),
+                                     ("nddct3", 512, np.float64), ("nddct3", 4096, np.float32)])
+def test_mirror_paired_first_pass(hs, op, n, rd, capfd):
+    """C2R / DCT-III on the small-radix-first schedules (4.8.8 / 4.8.8.8 / 8.16.16): pass 0 runs butterflies i and NB - i in one
+    thread, fed by the zip of bins j and N - j straight from global memory (no prologue round trip through shared memory)."""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run(op, n, (3, n), 1, rd, seed=n)
+        hs.run(op, n, (n, 5), 0, rd, seed=n + 1, norm="none")
+    finally:
+        del os.environ["NDFB_TRACE"]
+    assert capfd.readouterr().err.count("fam=R") == 2

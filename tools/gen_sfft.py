@@ -73,7 +73,7 @@ def make(f64, N, TL, rad, L, cols, fam, minb=None, always_smem=False):
     smem = L * npad(N, rad[0]) * cs if (len(rad) > 1 or always_smem) else 0
     E = max(-(-(N // r) // TL) * r for r in rad)
     if minb is None:
-        regs = E * (4 if f64 else 2) + (32 if fam == 1 else (56 if f64 else 44))
+        regs = E * (4 if f64 else 2) + (32 if fam >= 1 else (56 if f64 else 44))
         regs = min(regs, 255)
         minb = max(1, min(65536 // (T * regs), (227 * 1024) // max(smem, 1) if smem else 8, 8))
     return dict(f64=f64, N=N, TL=TL, rad=rad + [1] * (4 - len(rad)), L=L, cols=cols, minb=minb, T=T, smem=smem, E=E, fam=fam)
@@ -150,10 +150,33 @@ def c2c_cols(f64):
     return dedup(out)
 
 
+# core lengths whose family-B schedule is also instantiated small-radix-FIRST (4.8.8.8): pass 0 then has two butterflies per
+# thread and the C2R / DCT-III prologue runs mirror-paired from registers (sfft_kernel.cuh: kMirrorPro)
+REVERSED = {1: (256, 2048), 0: (2048,)}
+
+
 def real_entries(f64):
     out = []
     rs = 8 if f64 else 4
     cs = 2 * rs
+    for N in REVERSED[f64]:
+        TL, rad = pow2_schedule(N, f64, 1)
+        if rad[-1] >= rad[0]:
+            continue
+        rev = rad[::-1]
+        out.append(make(f64, N, TL, rev, rows_L(N, TL, rev[0], cs), 0, 2, always_smem=True))
+        nfit = 0
+        for L in (32, 16, 8, 4, 2):
+            if L * rs > 128:
+                continue
+            e = make(f64, N, TL, rev, L, 1, 2, always_smem=True)
+            tmax = 1024 if e["E"] * (4 if f64 else 2) <= 32 else 512
+            if e["T"] > tmax or e["T"] < 32 or e["smem"] > 200 * 1024:
+                continue
+            out.append(e)
+            nfit += 1
+            if nfit == 2:
+                break
     for fam in (0, 1):
         for N in [64, 128, 256, 512, 1024, 2048, 4096, 4095, 132, 264]:
             sc = schedule(N, f64, fam)
