@@ -690,7 +690,10 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
     }
     // family 2 = family B with the small radix FIRST: only for the kinds whose prologue pairs bins j and N-j (C2R, DCT-III),
     // where it lets pass 0 run mirror-paired from registers (kMirrorPro); preferred there, ignored elsewhere
-    const bool wants_rev = (rkind == RK_C2R || rkind == RK_DCT3) && !std::getenv("NDFB_NO_MIRROR_PRO");
+    // Measured on B200 (profiles/round2/r2m_ab_mirror_first_pass.txt): the saved prologue round trip does not pay for the
+    // radix-4-first schedule (c3 ndifft_r2c 0.426 -> 0.460 ms, DCT-III rows 0.109 = 0.109 ms, columns 0.146 -> 0.141 ms),
+    // so it is opt-in: NDFB_MIRROR_PRO=1.
+    const bool wants_rev = (rkind == RK_C2R || rkind == RK_DCT3) && std::getenv("NDFB_MIRROR_PRO") != nullptr;
     const int pref = wants_rev ? 2 : preferred_family(f64, N, cols, true);
     const RsfftEntry* best = nullptr;
     for (const Tab& t : tabs)

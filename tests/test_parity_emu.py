@@ -641,9 +641,11 @@ def test_mirror_paired_first_pass(hs, op, n, rd, capfd):
     thread, fed by the zip of bins j and N - j straight from global memory (no prologue round trip through shared memory)."""
     import os
     os.environ["NDFB_TRACE"] = "1"
+    os.environ["NDFB_MIRROR_PRO"] = "1"          # opt-in: measured slower than the big-radix-first schedules on B200
     try:
         hs.run(op, n, (3, n), 1, rd, seed=n)
         hs.run(op, n, (n, 5), 0, rd, seed=n + 1, norm="none")
     finally:
         del os.environ["NDFB_TRACE"]
+        del os.environ["NDFB_MIRROR_PRO"]
     assert capfd.readouterr().err.count("fam=R") == 2
