@@ -41,6 +41,8 @@ struct SyncHint {
     void clear() { *this = SyncHint(); }
 };
 static thread_local SyncHint g_sync_hint;
+// a hint is for the NEXT call only: whatever way that call ends (argument error included), the hint must not leak into a later one
+struct SyncHintScope { ~SyncHintScope() { g_sync_hint.clear(); } };
 static thread_local bool g_trans_next = false;   // launch_c2c -> launch_sfft: run the entry as a transposing rows kernel
 
 // ------------------------------------------------------------------------------------------------------
@@ -1820,6 +1822,8 @@ static int exec_common(const ndfb_plan* plan, int op, int norm, double extra_sca
                        const void* in, void* out, int ndim, const size_t* shape_in, const ptrdiff_t* strides_in,
                        const size_t* shape_out, const ptrdiff_t* strides_out, int axis, int mem, void* stream,
                        int nblk_ptr, void* const* blk_ptrs) {
+    SyncHintScope hint_scope;
+    (void)hint_scope;
     if (!plan || !shape_in || !strides_in || !shape_out || !strides_out) return fail(NDFB_E_INVALID, "null argument");
     if (ndim < 1 || ndim > NDFB_MAX_DIMS) return fail(NDFB_E_INVALID, "ndim %d outside 1..%d", ndim, NDFB_MAX_DIMS);
     if (norm != NDFB_NORM_NONE && norm != NDFB_NORM_DEFAULT) return fail(NDFB_E_INVALID, "unknown norm %d", norm);
@@ -1866,6 +1870,9 @@ int ndfb_exec(const ndfb_plan* plan, int op, int norm, const void* in, void* out
 
 int ndfb_exec_chain(const ndfb_step* steps, int nsteps, const void* in, void* out, int ndim, const size_t* shape_in,
                     const ptrdiff_t* strides_in, const size_t* shape_out, const ptrdiff_t* strides_out, int mem, void* stream) {
+    SyncHintScope hint_scope;   // launch hints do not apply to chains
+    (void)hint_scope;
+    if (g_sync_hint.signal_cnt || g_sync_hint.wait_cnt) return fail(NDFB_E_UNSUPPORTED, "launch signal / wait hints apply to single ndfb_exec calls, not to chains");
     if (!steps || nsteps < 1 || nsteps > 16) return fail(NDFB_E_INVALID, "1..16 steps expected");
     if (!shape_in || !strides_in || !shape_out || !strides_out) return fail(NDFB_E_INVALID, "null argument");
     if (ndim < 1 || ndim > NDFB_MAX_DIMS) return fail(NDFB_E_INVALID, "ndim %d outside 1..%d", ndim, NDFB_MAX_DIMS);
