@@ -264,9 +264,22 @@ struct SfftUntil {
 // two butterflies per thread, thread i takes butterflies i and NB - i (thread 0: 0 and NB/2), whose outputs are exactly each
 // other's mirror bins (k = b + q NB  <->  N - k = (NB - b) + (r-1-q) NB).  The pair epilogue then runs from registers: no
 // write of the spectrum to shared memory, no barrier, no read-back — one shared-memory round trip less per lane.
+// (any EVEN number of butterflies per thread works the same way: G/2 mirror pairs per thread)
 template <class S>
-constexpr bool kMirrorEpi = S::NP >= 2 && S::G(S::NP - 1) == 2 && S::nbf(S::NP - 1) == 2 * S::TL && S::nbf(S::NP - 1) % 2 == 0 &&
-                            S::radix(S::NP - 1) % 2 == 0;
+constexpr bool kMirrorEpi = S::NP >= 2 && S::G(S::NP - 1) % 2 == 0 && S::nbf(S::NP - 1) == S::G(S::NP - 1) * S::TL &&
+                            S::nbf(S::NP - 1) % 2 == 0 && S::radix(S::NP - 1) % 2 == 0;
+// One butterfly per thread in the last pass: the mirror butterfly lives in ANOTHER thread.  For contiguous rows the butterflies
+// are dealt so that lanes t and t ^ 16 of a warp hold butterflies b and NB - b, and the partner's outputs arrive by
+// __shfl_xor_sync: the pair epilogue again runs from registers, with warp shuffles instead of a shared-memory round trip.
+// Measured on B200 (profiles/round2/r2n_ab_pair_epilogue.jsonl): the shuffle form LOSES 1.3-1.75x against the shared-memory
+// epilogue (32 SHFL.32 per thread for eight c128 values move a quarter of what eight LDS.128 move per instruction, and both
+// partners repeat the pair arithmetic), so it is compiled only with -DNDFB_SHUFFLE_EPI=1; the in-thread mirror pairs gain 2-12 %.
+#ifndef NDFB_SHUFFLE_EPI
+#define NDFB_SHUFFLE_EPI 0
+#endif
+template <class S>
+constexpr bool kShuffleEpi = NDFB_SHUFFLE_EPI && S::NP >= 2 && S::G(S::NP - 1) == 1 && S::nbf(S::NP - 1) == S::TL && S::TL % 32 == 0 &&
+                             S::radix(S::NP - 1) % 2 == 0;
 
 // The same pairing on the FIRST pass for the kinds whose inputs come in mirror pairs (C2R, DCT-III: slots j and N-j are built
 // from the same two spectrum bins): schedules that START with the small radix (4.8.8.8) give pass 0 two butterflies per thread.
@@ -1038,65 +1051,108 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     };
 
     Cx<R> v[S::E];
-    if constexpr (PAIR_EPI && kMirrorEpi<S>) {
-        constexpr int LP = S::NP - 1, r = S::radix(LP), P = S::before(LP), NB = S::nbf(LP);
-        SfftUntil<R, S, L, COLS, 0, LP, STAGE_IN || PAIR_PRO>::run(c, v, tw, load, store);
-        const int i = c.i;
-        const int b0 = i, b1 = i == 0 ? NB / 2 : NB - i;
-#pragma unroll
-        for (int q = 0; q < r; ++q) {
-            v[q] = c.smem[c.addr(b0 + q * NB)];
-            v[r + q] = c.smem[c.addr(b1 + q * NB)];
+    // bins k and k2 = N - k of the length-2N real DFT from Z[k] = zk and Z[N-k] = zm (k = 0: zm = Z[0], k2 = N);
+    // both == false: only bin k is produced (its mirror is another thread's)
+    auto emit = [&](int k, Cx<R> zk, Cx<R> zm, bool both) {
+        const int k2 = N - k;
+        const Cx<R> zc = cconj(zm);
+        const Cx<R> w = ldg(&tabA[k]);
+        const Cx<R> s = cadd(zk, zc), d = cmul(w, csub(zk, zc));
+        const Cx<R> X = cmake<R>((R)0.5 * (s.x + d.y), (R)0.5 * (s.y - d.x));
+        const Cx<R> X2 = cmake<R>((R)0.5 * (s.x - d.y), (R)-0.5 * (s.y + d.x));
+        if (!valid) return;
+        const bool two = both && k2 != k;
+        if (KIND == RK_R2C) {
+            out_c[(long long)k * os_axis] = cmake<R>(sc * X.x, sc * X.y);
+            if (two) out_c[(long long)k2 * os_axis] = cmake<R>(sc * X2.x, sc * X2.y);
+        } else if (KIND == RK_DCT1) {
+            out_r[(long long)k * os_axis] = (R)0.5 * sc * X.x;
+            if (two) out_r[(long long)k2 * os_axis] = (R)0.5 * sc * X2.x;
+        } else if (KIND == RK_DCT2) {
+            const Cx<R> A = cmul(X, ldg(&tabB[k]));
+            out_r[(long long)k * os_axis] = sc * A.x;
+            if (k > 0 && k < N) out_r[(long long)(n - k) * os_axis] = -sc * A.y;
+            if (two) {
+                const Cx<R> A2 = cmul(X2, ldg(&tabB[k2]));
+                out_r[(long long)k2 * os_axis] = sc * A2.x;
+                if (k2 > 0 && k2 < N) out_r[(long long)(n - k2) * os_axis] = -sc * A2.y;
+            }
         }
-        {
+    };
+    if constexpr (PAIR_EPI && kMirrorEpi<S>) {
+        constexpr int LP = S::NP - 1, r = S::radix(LP), P = S::before(LP), NB = S::nbf(LP), HG = S::G(LP) / 2;
+        SfftUntil<R, S, L, COLS, 0, LP, STAGE_IN || PAIR_PRO>::run(c, v, tw, load, store);
+        // pair m of this thread: butterflies p = i + TL m and NB - p (p = 0: butterflies 0 and NB/2, both their own mirror)
+#pragma unroll
+        for (int m = 0; m < HG; ++m) {
+            const int p = c.i + S::TL * m;
+            const int b0 = p, b1 = p == 0 ? NB / 2 : NB - p;
+            Cx<R>* u = &v[2 * m * r];
+#pragma unroll
+            for (int q = 0; q < r; ++q) {
+                u[q] = c.smem[c.addr(b0 + q * NB)];
+                u[r + q] = c.smem[c.addr(b1 + q * NB)];
+            }
             const Cx<R>* __restrict__ t0 = tw + S::twoff(LP) + (b0 % P);
             const Cx<R>* __restrict__ t1 = tw + S::twoff(LP) + (b1 % P);
 #pragma unroll
             for (int q = 1; q < r; ++q) {
-                v[q] = cmul(v[q], ldg(&t0[(q - 1) * P]));
-                v[r + q] = cmul(v[r + q], ldg(&t1[(q - 1) * P]));
+                u[q] = cmul(u[q], ldg(&t0[(q - 1) * P]));
+                u[r + q] = cmul(u[r + q], ldg(&t1[(q - 1) * P]));
             }
+            Dft<R, r>::run(&u[0]);
+            Dft<R, r>::run(&u[r]);
+        }
+#pragma unroll
+        for (int m = 0; m < HG; ++m) {
+            const int p = c.i + S::TL * m;
+            Cx<R>* u = &v[2 * m * r];
+            if (p != 0) {
+#pragma unroll
+                for (int q = 0; q < r; ++q) emit(p + q * NB, u[q], u[r + (r - 1 - q)], true);
+            } else {
+                emit(0, u[0], u[0], true);                                         // bins 0 and N, both from Z[0]
+#pragma unroll
+                for (int q = 1; q < r / 2; ++q) emit(q * NB, u[q], u[r - q], true);
+                emit((r / 2) * NB, u[r / 2], u[r / 2], true);                      // k = N/2 pairs with itself
+#pragma unroll
+                for (int q = 0; q < r / 2; ++q) emit(NB / 2 + q * NB, u[r + q], u[r + (r - 1 - q)], true);
+            }
+        }
+        return;
+    }
+    if constexpr (PAIR_EPI && !COLS && !kMirrorEpi<S> && kShuffleEpi<S>) {
+        constexpr int LP = S::NP - 1, r = S::radix(LP), P = S::before(LP), NB = S::nbf(LP);
+        SfftUntil<R, S, L, COLS, 0, LP, STAGE_IN || PAIR_PRO>::run(c, v, tw, load, store);
+        // deal the butterflies: warp w of the lane, lanes 0..15 take 16 w + t, lanes 16..31 take NB - 16 w - (t - 16)
+        // (NB itself does not exist: lane 16 of warp 0 takes NB/2, which like 0 is its own mirror)
+        const int w = c.i >> 5, t = c.i & 31;
+        const bool self = (w == 0) && (t == 0 || t == 16);
+        const int b = t < 16 ? 16 * w + t : (self ? NB / 2 : NB - 16 * w - (t - 16));
+#pragma unroll
+        for (int q = 0; q < r; ++q) v[q] = c.smem[c.addr(b + q * NB)];
+        {
+            const Cx<R>* __restrict__ t0 = tw + S::twoff(LP) + (b % P);
+#pragma unroll
+            for (int q = 1; q < r; ++q) v[q] = cmul(v[q], ldg(&t0[(q - 1) * P]));
         }
         Dft<R, r>::run(&v[0]);
-        Dft<R, r>::run(&v[r]);
-        // bins k and k2 = N - k of the length-2N real DFT from Z[k] = zk and Z[N-k] = zm (k = 0: zm = Z[0], k2 = N)
-        auto emit = [&](int k, Cx<R> zk, Cx<R> zm) {
-            const int k2 = N - k;
-            const Cx<R> zc = cconj(zm);
-            const Cx<R> w = ldg(&tabA[k]);
-            const Cx<R> s = cadd(zk, zc), d = cmul(w, csub(zk, zc));
-            const Cx<R> X = cmake<R>((R)0.5 * (s.x + d.y), (R)0.5 * (s.y - d.x));
-            const Cx<R> X2 = cmake<R>((R)0.5 * (s.x - d.y), (R)-0.5 * (s.y + d.x));
-            if (!valid) return;
-            const bool two = k2 != k;
-            if (KIND == RK_R2C) {
-                out_c[(long long)k * os_axis] = cmake<R>(sc * X.x, sc * X.y);
-                if (two) out_c[(long long)k2 * os_axis] = cmake<R>(sc * X2.x, sc * X2.y);
-            } else if (KIND == RK_DCT1) {
-                out_r[(long long)k * os_axis] = (R)0.5 * sc * X.x;
-                if (two) out_r[(long long)k2 * os_axis] = (R)0.5 * sc * X2.x;
-            } else {  // RK_DCT2
-                const Cx<R> A = cmul(X, ldg(&tabB[k]));
-                out_r[(long long)k * os_axis] = sc * A.x;
-                if (k > 0 && k < N) out_r[(long long)(n - k) * os_axis] = -sc * A.y;
-                if (two) {
-                    const Cx<R> A2 = cmul(X2, ldg(&tabB[k2]));
-                    out_r[(long long)k2 * os_axis] = sc * A2.x;
-                    if (k2 > 0 && k2 < N) out_r[(long long)(n - k2) * os_axis] = -sc * A2.y;
-                }
-            }
-        };
-        if (i != 0) {
+        // Z[N - k] for k = b + q NB is the partner's output r-1-q (own output (r-q) % r for b = 0, r-1-q for b = NB/2)
+        Cx<R> zm[r];
 #pragma unroll
-            for (int q = 0; q < r; ++q) emit(b0 + q * NB, v[q], v[r + (r - 1 - q)]);
-        } else {
-            emit(0, v[0], v[0]);                                        // bins 0 and N, both from Z[0]
-#pragma unroll
-            for (int q = 1; q < r / 2; ++q) emit(q * NB, v[q], v[r - q]);
-            emit((r / 2) * NB, v[r / 2], v[r / 2]);                     // k = N/2 pairs with itself
-#pragma unroll
-            for (int q = 0; q < r / 2; ++q) emit(NB / 2 + q * NB, v[r + q], v[r + (r - 1 - q)]);
+        for (int q = 0; q < r; ++q) {
+            Cx<R> got;
+            got.x = __shfl_xor_sync(0xffffffffu, v[r - 1 - q].x, 16);
+            got.y = __shfl_xor_sync(0xffffffffu, v[r - 1 - q].y, 16);
+            zm[q] = got;
         }
+        if (self) {
+#pragma unroll
+            for (int q = 0; q < r; ++q) zm[q] = (b == 0) ? v[(r - q) % r] : v[r - 1 - q];
+        }
+#pragma unroll
+        for (int q = 0; q < r; ++q) emit(b + q * NB, v[q], zm[q], false);
+        if (b == 0) emit(0, v[0], v[0], true);        // also bin N (bin 0 is written twice with the same value)
         return;
     }
     if constexpr (MIRROR_PRO) {

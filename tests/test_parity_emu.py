@@ -649,3 +649,14 @@ def test_mirror_paired_first_pass(hs, op, n, rd, capfd):
         del os.environ["NDFB_TRACE"]
         del os.environ["NDFB_MIRROR_PRO"]
     assert capfd.readouterr().err.count("fam=R") == 2
+
+
+@pytest.mark.parametrize("op,n,rd", [("ndfft_r2c", 1024, np.float64), ("nddct2", 1024, np.float64), ("nddct1", 513, np.float64),
+                                     ("ndfft_r2c", 8192, np.float32), ("nddct2", 2048, np.float64), ("ndfft_r2c", 2048, np.float32),
+                                     ("nddct2", 1024, np.float32), ("ndfft_r2c", 256, np.float64)])
+def test_pair_epilogue_from_registers_all_schedules(hs, op, n, rd):
+    """One butterfly per thread in the last pass (512-point f64 core 8.8.8, 4096-point f32 core 16.16.16): mirror outputs
+    arrive by warp shuffle (rows).  Four or eight butterflies per thread (1024-point f64 core 8.8.8.2, f32 cores 16.16.4 /
+    16.16.2): G/2 in-thread mirror pairs.  Columns of the one-butterfly schedules keep the shared-memory epilogue."""
+    hs.run(op, n, (3, n), 1, rd, seed=n)
+    hs.run(op, n, (n, 5), 0, rd, seed=n + 1, norm="none")
