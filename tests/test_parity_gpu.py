@@ -732,3 +732,51 @@ def test_jit_lengths_real_kinds(dev, op, n, capfd):
     if "run-time schedule compilation unavailable" in err:
         pytest.skip("libnvrtc not usable on this box")
     assert err.count("[ndfb] rsfft") == 2 and err.count(" jit") >= 2, err
+
+
+# ---- round-2 kernels and entry points on the GPU ----
+def test_rows_bulk_async_kernel_gpu(dev, capfd):
+    """The persistent TMA + mbarrier row kernel (opt-in) gives the bits of the register-resident kernel."""
+    import os
+    be = dev.be
+    rng = np.random.default_rng(21)
+    for n, rd, lanes in ((8192, np.float32, 700), (2048, np.float64, 1300), (1024, np.float32, 2051)):
+        x = (rng.uniform(-1, 1, (lanes, n)) + 1j * rng.uniform(-1, 1, (lanes, n))).astype(cdt(rd))
+        xd = torch.from_numpy(x).cuda()
+        y0 = torch.empty_like(xd); y1 = torch.empty_like(xd)
+        h = be.FftHandler(n, rd)
+        be.ndfft(xd, y0, h, 1)
+        os.environ["NDFB_ROWS_BULK"] = "2"; os.environ["NDFB_TRACE"] = "1"
+        try:
+            be.ndfft(xd, y1, h, 1)
+            be.ndifft(y1, xd, h, 1)
+        finally:
+            del os.environ["NDFB_ROWS_BULK"]; del os.environ["NDFB_TRACE"]
+        assert capfd.readouterr().err.count("rows bulk-async persistent") == 2
+        assert torch.equal(y0, y1)
+        assert orc.rel_l2(xd.cpu().numpy(), x) <= TOL[np.dtype(rd)]
+
+
+def test_device_memory_and_stream_helpers(dev):
+    """ndfb_device_alloc / ndfb_memcpy / ndfb_stream_*: what the Rust shim's DeviceArray and Stream are built on; pageable
+    uploads and downloads above 4 MiB go through the pinned ring."""
+    import ctypes
+    from ndrustfft_b200 import _lib
+    be = dev.be
+    dll = be.lib.dll
+    rng = np.random.default_rng(22)
+    n, lanes = 1024, 1500                                   # 24 MiB c128: ring path
+    x = rng.uniform(-1, 1, (lanes, n)) + 1j * rng.uniform(-1, 1, (lanes, n))
+    y = np.zeros_like(x)
+    st = ctypes.c_void_p(); din = ctypes.c_void_p(); dout = ctypes.c_void_p()
+    be.lib.check(dll.ndfb_stream_create(ctypes.byref(st), 0))
+    be.lib.check(dll.ndfb_device_alloc(ctypes.byref(din), x.nbytes, 0))
+    be.lib.check(dll.ndfb_device_alloc(ctypes.byref(dout), x.nbytes, 0))
+    be.lib.check(dll.ndfb_memcpy(din, ctypes.c_void_p(x.ctypes.data), x.nbytes, 0, 0, st))
+    h = be.FftHandler(n)
+    SZ, PD = ctypes.c_size_t * 2, ctypes.c_ssize_t * 2
+    be.lib.check(dll.ndfb_exec(h._plan, _lib.OP_FFT, _lib.NORM_DEFAULT, din, dout, 2, SZ(lanes, n), PD(n, 1), SZ(lanes, n), PD(n, 1), 1, _lib.MEM_DEVICE, st))
+    be.lib.check(dll.ndfb_memcpy(ctypes.c_void_p(y.ctypes.data), dout, x.nbytes, 1, 0, st))
+    be.lib.check(dll.ndfb_stream_sync(st))
+    assert orc.rel_l2(y, np.fft.fft(x, axis=1)) < 1e-12
+    dll.ndfb_device_free(din); dll.ndfb_device_free(dout); dll.ndfb_stream_destroy(st)
