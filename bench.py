@@ -175,6 +175,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks, which throttles pocketfft's worker pool (measured: 3-5x slower): the CPU
+    # arm gets every host core it can use, set before numpy / scipy are first imported
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     K, W = max(1, args.steps), max(0, args.warmup)
     gf, dt, cores, sample = cpu_c3_run(K, W)
     line = {
