@@ -29,6 +29,9 @@ $(OBJDIR)/cuda/ndfft_b200.o: $(CSRC)/ndfft_b200.cu $(HDRS) $(CSRC)/jit_sources.i
 	@mkdir -p $(OBJDIR)/cuda
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
+# the software-pipelined column kernels have headers of their own (not in KHDRS: editing them rebuilds one file)
+$(OBJDIR)/cuda/sfft_inst_pipe.o $(OBJDIR)/emu/sfft_inst_pipe.o: $(CSRC)/pipe_kernel.cuh $(CSRC)/pipe_inst.h
+
 $(OBJDIR)/cuda/%.o: $(CSRC)/%.cu $(KHDRS)
 	@mkdir -p $(OBJDIR)/cuda
 	$(NVCC) $(NVFLAGS) -c -o $@ $<

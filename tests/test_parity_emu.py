@@ -660,3 +660,38 @@ def test_pair_epilogue_from_registers_all_schedules(hs, op, n, rd):
     16.16.2): G/2 in-thread mirror pairs.  Columns of the one-butterfly schedules keep the shared-memory epilogue."""
     hs.run(op, n, (3, n), 1, rd, seed=n)
     hs.run(op, n, (n, 5), 0, rd, seed=n + 1, norm="none")
+
+
+def test_pipelined_column_kernel(hs, capfd):
+    """Software-pipelined persistent column kernel (pipe_kernel.cuh: cp.async staging of the next tile, split re / im exchange;
+    plain copies under the emulator): lane-adjacent input (strided axis) and row input (contiguous axis written lane-interleaved),
+    several tiles per CTA, forward / inverse, full and partial passes (360 = 6.6.10), both precisions."""
+    import os
+    os.environ.update({"NDFB_PIPE": "2", "NDFB_TRACE": "1"})
+    try:
+        hs.run("ndfft", 64, (64, 12), 0, np.float32, seed=1)                 # INMODE 0: 3 tiles of 4 lanes
+        hs.run("ndifft", 512, (512, 8), 0, np.float32, seed=2)               # 16.16.2
+        hs.run("ndfft", 256, (2, 256, 8), 1, np.float32, seed=3, norm="none")
+        hs.run("ndifft", 64, (64, 6), 0, np.float64, seed=4)                 # f64 8.8, L = 2
+        hs.run("ndfft", 512, (512, 4), 0, np.float64, seed=5)
+        hs.run("ndfft", 360, (360, 4), 0, np.float64, seed=6)                # partial passes
+        err = capfd.readouterr().err
+        assert err.count("cols pipelined") == 6, err
+        assert err.count("in=lane-adjacent") == 6, err
+    finally:
+        os.environ.pop("NDFB_PIPE", None); os.environ.pop("NDFB_TRACE", None)
+
+
+def test_pipelined_column_kernel_four_step(hs, capfd):
+    """Both passes of a two-pass split on the pipelined kernel: pass 1 reads lane-adjacent rows and applies the four-step twiddle
+    in its store, pass 2 reads contiguous workspace rows (row staging layout) and stores lane-interleaved."""
+    import os
+    os.environ.update({"NDFB_PIPE": "2", "NDFB_TRACE": "1", "NDFB_FS_CAP": "512", "NDFB_FS_N1": "64"})
+    try:
+        hs.run("ndfft", 64 * 512, (2, 64 * 512), 1, np.float32, seed=7)
+        hs.run("ndifft", 64 * 512, (1, 64 * 512), 1, np.float64, seed=8)
+        err = capfd.readouterr().err
+        assert err.count("in=lane-adjacent") == 2 and err.count("in=rows") == 2, err
+    finally:
+        for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1"):
+            os.environ.pop(k, None)

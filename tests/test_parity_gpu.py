@@ -757,6 +757,47 @@ def test_rows_bulk_async_kernel_gpu(dev, capfd):
         assert orc.rel_l2(xd.cpu().numpy(), x) <= TOL[np.dtype(rd)]
 
 
+def test_pipelined_column_kernel_gpu(dev, capfd):
+    """The software-pipelined persistent column kernel (cp.async staging + split exchange) gives the bits of the register-resident
+    kernel: lane-adjacent input (strided axis), both precisions, the tile shapes of c5b / c2 / long f64 columns; then a two-pass
+    split whose both passes take it (pass 2 = contiguous workspace rows in, lane-interleaved out)."""
+    import os
+    be = dev.be
+    rng = np.random.default_rng(22)
+    for n, rd, lanes in ((4096, np.float32, 1200), (8192, np.float32, 600), (2048, np.float64, 1184), (4096, np.float64, 596), (512, np.float32, 64)):
+        x = (rng.uniform(-1, 1, (n, lanes)) + 1j * rng.uniform(-1, 1, (n, lanes))).astype(cdt(rd))
+        xd = torch.from_numpy(x).cuda()
+        y0 = torch.empty_like(xd); y1 = torch.empty_like(xd)
+        h = be.FftHandler(n, rd)
+        os.environ["NDFB_PIPE"] = "0"; os.environ["NDFB_STRIDED_FOURSTEP"] = "0"
+        try:
+            be.ndfft(xd, y0, h, 0)
+            os.environ["NDFB_PIPE"] = "2"; os.environ["NDFB_TRACE"] = "1"
+            be.ndfft(xd, y1, h, 0)
+            be.ndifft(y1, xd, h, 0)
+        finally:
+            for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_STRIDED_FOURSTEP"):
+                os.environ.pop(k, None)
+        assert capfd.readouterr().err.count("cols pipelined") == 2
+        assert torch.equal(y0, y1)
+        assert orc.rel_l2(xd.cpu().numpy(), x) <= TOL[np.dtype(rd)]
+    n = 1 << 24
+    x = _rand((6, n), np.float32, True, 77)
+    h = be.FftHandler(n, np.float32)
+    y0 = torch.empty_like(x); y1 = torch.empty_like(x)
+    os.environ["NDFB_PIPE"] = "0"
+    try:
+        be.ndfft(x, y0, h, 1)
+        os.environ["NDFB_PIPE"] = "2"; os.environ["NDFB_TRACE"] = "1"
+        be.ndfft(x, y1, h, 1)
+    finally:
+        for k in ("NDFB_PIPE", "NDFB_TRACE"):
+            os.environ.pop(k, None)
+    err = capfd.readouterr().err
+    assert err.count("in=lane-adjacent") == 1 and err.count("in=rows") == 1, err
+    assert torch.equal(y0, y1)
+
+
 def test_device_memory_and_stream_helpers(dev):
     """ndfb_device_alloc / ndfb_memcpy / ndfb_stream_*: what the Rust shim's DeviceArray and Stream are built on; pageable
     uploads and downloads above 4 MiB go through the pinned ring."""

@@ -280,6 +280,22 @@ def bulk_entries():
     return out
 
 
+def pipe_entries():
+    """Software-pipelined persistent column kernels (pipe_kernel.cuh): tiles that own a whole SM (both passes of the 2^24-point
+    rows of BASELINE c5b, the long f64 columns), plus a few small schedules for the emulator / GPU parity tests."""
+    out = []
+    prod = [(0, 4096, 4), (0, 8192, 2), (0, 2048, 8), (1, 2048, 4), (1, 4096, 2), (1, 1024, 8)]
+    small = [(0, 64, 4), (0, 512, 4), (0, 256, 4), (1, 64, 2), (1, 512, 4), (1, 360, 2)]
+    for f64, N, L in prod + small:
+        sc = schedule(N, f64, 1) or schedule(N, f64, 0)
+        TL, rad = sc
+        rad = list(rad) + [1] * (4 - len(rad))
+        R = "double" if f64 else "float"
+        for inmode in (0, 1):
+            out.append(f"    SFFT_PIPE_ENTRY({R}, {f64}, {N}, {TL}, {rad[0]}, {rad[1]}, {rad[2]}, {rad[3]}, {L}, {inmode}, 1),  // T={TL * L}")
+    return out
+
+
 def dedup(entries):
     seen, out = set(), []
     for e in entries:
@@ -298,15 +314,20 @@ def fmt(e, macro, extra=""):
             f"  // T={e['T']} smem={e['smem']} E={e['E']}")
 
 
+WRITTEN = set()
+
+
 def write(path, lines):
-    with open(os.path.join(OUT, path), "w") as f:
-        f.write("\n".join(lines) + "\n")
+    """Unchanged files keep their mtime (make would otherwise rebuild ~900 kernel instances)."""
+    WRITTEN.add(path)
+    full, text = os.path.join(OUT, path), "\n".join(lines) + "\n"
+    if os.path.exists(full) and open(full).read() == text:
+        return
+    with open(full, "w") as f:
+        f.write(text)
 
 
 def main():
-    for f in os.listdir(OUT):
-        if f.startswith(("sfft_inst_", "rsfft_inst_", "bsfft_inst_", "fs2_inst")) and f.endswith(".cu"):
-            os.remove(os.path.join(OUT, f))
     total = 0
     head = ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "sfft_inst.h"', "", "namespace ndfb {", ""]
     groups = {"f32_rows": c2c_rows(0), "f32_cols": c2c_cols(0), "f64_rows": c2c_rows(1), "f64_cols": c2c_cols(1)}
@@ -323,6 +344,10 @@ def main():
     ents = bulk_entries()
     write("sfft_inst_bulk.cu", head + ["const SfftBulkEntry kSfftBulk[] = {"] + ents + ["};", f"const int kSfftBulk_count = {len(ents)};", "", "}  // namespace ndfb"])
     total += len(ents)
+    ents = pipe_entries()
+    write("sfft_inst_pipe.cu", ["// GENERATED by tools/gen_sfft.py — do not edit.", '#include "pipe_inst.h"', "", "namespace ndfb {", "",
+                                "const SfftPipeEntry kSfftPipe[] = {"] + ents + ["};", f"const int kSfftPipe_count = {len(ents)};", "", "}  // namespace ndfb"])
+    total += len(ents)
     ents = fs2_entries()
     write("fs2_inst.cu", head + ["const Fs2Entry kFs2[] = {"] + ents + ["};", f"const int kFs2_count = {len(ents)};", "", "}  // namespace ndfb"])
     total += len(ents)
@@ -336,6 +361,9 @@ def main():
             total += len(ents)
             rnames.append(nm)
     write("rsfft_tables.inc", ["// GENERATED by tools/gen_sfft.py — do not edit."] + [f"RSFFT_TABLE({nm})" for nm in rnames])
+    for f in os.listdir(OUT):      # instance files of an earlier rule set
+        if f.startswith(("sfft_inst_", "rsfft_inst_", "bsfft_inst_", "fs2_inst")) and f.endswith(".cu") and f not in WRITTEN:
+            os.remove(os.path.join(OUT, f))
     print("generated", total, "instances")
     if "-v" in sys.argv:
         for name, ents in groups.items():
