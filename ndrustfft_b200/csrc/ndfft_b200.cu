@@ -581,51 +581,58 @@ static int try_pipe(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, long 
     *done = 0;
     const int mode = pipe_mode();
     if (!mode || s.os_blk || s.nblk_ptr || s.trans || g_sync_hint.wait_cnt || s.dims.empty() || (int)s.dims.size() > kMaxBatchDims) return 0;
-    if (mode < 2 && !(e && e->smem * 2 > (size_t)(227 * 1024))) return 0;
+    if (mode < 2 && !(e && e->cols && e->smem * 2 > (size_t)(227 * 1024))) return 0;   // rows: only on request (A/B runs, tests)
     const size_t cs = sizeof(Cx<R>);
     if ((uintptr_t)s.in % 16) return 0;
     const int N = s.core->t.N;
     const int sms = dev_sm_count(p->device);
+    // contiguous rows in AND out take the one-lane tiles (the tile is one row: no lane interleaving to pay for), every other
+    // layout the widest tile (full sectors per tile row)
+    const bool rows_io = s.is_axis == 1 && s.os_axis == 1;
+    const SfftPipeEntry* pe = nullptr;
     for (int i = 0; i < kSfftPipe_count; ++i) {
-        const SfftPipeEntry* pe = &kSfftPipe[i];
-        if (pe->f64 != (sizeof(R) == 8 ? 1 : 0) || pe->N != N) continue;
-        if (nlanes % pe->L || s.dims[0].size % pe->L) continue;              // every tile is full and lies in one row of the fastest batch dim
+        const SfftPipeEntry* c = &kSfftPipe[i];
+        if (c->f64 != (sizeof(R) == 8 ? 1 : 0) || c->N != N) continue;
+        if ((c->L == 1) != rows_io) continue;
+        if (const char* v = std::getenv("NDFB_PIPE_L")) { if (c->L != atoi(v)) continue; }   // measurement hook: tile width
+        if (nlanes % c->L || s.dims[0].size % c->L) continue;              // every tile is full and lies in one row of the fastest batch dim
         bool ok = true;
-        if (pe->inmode == 0) {
+        if (c->inmode == 0) {
             // L adjacent lanes = one 16-byte-aligned piece of every tile row
-            if (s.dims[0].is != 1 || (pe->L * cs) % 16 || (size_t)llabs_(s.is_axis) * cs % 16) ok = false;
+            if (s.dims[0].is != 1 || (c->L * cs) % 16 || (size_t)llabs_(s.is_axis) * cs % 16) ok = false;
             for (size_t d = 1; d < s.dims.size(); ++d) if ((size_t)llabs_(s.dims[d].is) * cs % 16) ok = false;
         } else {
             if (s.is_axis != 1 || ((size_t)N * cs) % 16) ok = false;
             for (auto& d : s.dims) if ((size_t)llabs_(d.is) * cs % 16) ok = false;
         }
         if (!ok) continue;
-        const long long ntiles = nlanes / pe->L;
-        if (ntiles > 0x7fffffffLL) continue;
-        if (mode < 2 && ntiles < 4LL * sms) continue;
-        SfftArgs a;
-        std::memset(&a, 0, sizeof a);
-        a.in = s.in; a.out = s.out; a.nlanes = nlanes; a.nbd = (int)s.dims.size();
-        for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
-        a.is_axis = s.is_axis; a.os_axis = s.os_axis; a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
-        a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
-        a.ntiles = ntiles;
-        SfftEntry proxy;
-        std::memset((void*)&proxy, 0, sizeof proxy);
-        for (int k = 0; k < 4; ++k) proxy.r[k] = pe->r[k];
-        proxy.twtotal = pe->twtotal;
-        void* twd = nullptr;
-        int rc = get_sfft_twiddles<R>(p, s.core, &proxy, &twd);
-        if (rc) return rc;
-        a.tw = twd;
-        const long long grid = std::min<long long>(ntiles, (long long)sms * std::max(1, pe->minb));
-        if (std::getenv("NDFB_TRACE"))
-            fprintf(stderr, "[ndfb] sfft %s N=%d cols pipelined (cp.async staging, split exchange) L=%d T=%d smem=%zu in=%s tiles=%lld grid=%lld radix=%d.%d.%d.%d\n",
-                    sizeof(R) == 8 ? "f64" : "f32", pe->N, pe->L, pe->threads, pe->smem, pe->inmode ? "rows" : "lane-adjacent", ntiles, grid, pe->r[0], pe->r[1], pe->r[2], pe->r[3]);
-        *done = 1;
-        return pe->launch(a, (unsigned)grid, stream);
+        if (!pe || c->L > pe->L) pe = c;
     }
-    return 0;
+    if (!pe) return 0;
+    const long long ntiles = nlanes / pe->L;
+    if (ntiles > 0x7fffffffLL) return 0;
+    if (mode < 2 && ntiles < 4LL * sms * std::max(1, pe->minb)) return 0;
+    SfftArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.in = s.in; a.out = s.out; a.nlanes = nlanes; a.nbd = (int)s.dims.size();
+    for (int d = 0; d < a.nbd; ++d) { a.bsz[d] = s.dims[d].size; a.bis[d] = s.dims[d].is; a.bos[d] = s.dims[d].os; }
+    a.is_axis = s.is_axis; a.os_axis = s.os_axis; a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
+    a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
+    a.ntiles = ntiles;
+    SfftEntry proxy;
+    std::memset((void*)&proxy, 0, sizeof proxy);
+    for (int k = 0; k < 4; ++k) proxy.r[k] = pe->r[k];
+    proxy.twtotal = pe->twtotal;
+    void* twd = nullptr;
+    int rc = get_sfft_twiddles<R>(p, s.core, &proxy, &twd);
+    if (rc) return rc;
+    a.tw = twd;
+    const long long grid = std::min<long long>(ntiles, (long long)sms * std::max(1, pe->minb));
+    if (std::getenv("NDFB_TRACE"))
+        fprintf(stderr, "[ndfb] sfft %s N=%d %s pipelined (cp.async staging, split exchange) L=%d T=%d smem=%zu in=%s tiles=%lld grid=%lld radix=%d.%d.%d.%d\n",
+                sizeof(R) == 8 ? "f64" : "f32", pe->N, rows_io ? "rows" : "cols", pe->L, pe->threads, pe->smem, pe->inmode ? "rows" : "lane-adjacent", ntiles, grid, pe->r[0], pe->r[1], pe->r[2], pe->r[3]);
+    *done = 1;
+    return pe->launch(a, (unsigned)grid, stream);
 }
 
 // C2C launch: the instantiated Stockham schedule when there is one, else the general tile kernel
@@ -682,7 +689,7 @@ static int launch_c2c(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
                 return be->launch(a, (unsigned)grid, stream);
             }
         }
-        if (cols && nlanes > 0) {
+        if ((cols || (s.is_axis == 1 && s.os_axis == 1)) && nlanes > 0 && !s.dims.empty()) {
             int done = 0;
             const int rc = try_pipe<R>(p, e, s, nlanes, stream, &done);
             if (rc || done) return rc;

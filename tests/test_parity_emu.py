@@ -678,6 +678,10 @@ def test_pipelined_column_kernel(hs, capfd):
         err = capfd.readouterr().err
         assert err.count("cols pipelined") == 6, err
         assert err.count("in=lane-adjacent") == 6, err
+        hs.run("ndfft", 256, (7, 256), 1, np.float32, seed=9)                # one-lane tiles: contiguous rows in and out
+        hs.run("ndifft", 512, (3, 5, 512), 2, np.float64, seed=10)
+        err = capfd.readouterr().err
+        assert err.count("rows pipelined") == 2 and err.count("L=1 ") == 2, err
     finally:
         os.environ.pop("NDFB_PIPE", None); os.environ.pop("NDFB_TRACE", None)
 

@@ -781,6 +781,22 @@ def test_pipelined_column_kernel_gpu(dev, capfd):
         assert capfd.readouterr().err.count("cols pipelined") == 2
         assert torch.equal(y0, y1)
         assert orc.rel_l2(xd.cpu().numpy(), x) <= TOL[np.dtype(rd)]
+    # one-lane tiles: contiguous rows in and out (opt-in)
+    for n, rd, lanes in ((8192, np.float32, 601), (4096, np.float64, 333)):
+        x = (rng.uniform(-1, 1, (lanes, n)) + 1j * rng.uniform(-1, 1, (lanes, n))).astype(cdt(rd))
+        xd = torch.from_numpy(x).cuda()
+        y0 = torch.empty_like(xd); y1 = torch.empty_like(xd)
+        h = be.FftHandler(n, rd)
+        os.environ["NDFB_PIPE"] = "0"
+        try:
+            be.ndfft(xd, y0, h, 1)
+            os.environ["NDFB_PIPE"] = "2"; os.environ["NDFB_TRACE"] = "1"
+            be.ndfft(xd, y1, h, 1)
+        finally:
+            for k in ("NDFB_PIPE", "NDFB_TRACE"):
+                os.environ.pop(k, None)
+        assert capfd.readouterr().err.count("rows pipelined") == 1
+        assert torch.equal(y0, y1)
     n = 1 << 24
     x = _rand((6, n), np.float32, True, 77)
     h = be.FftHandler(n, np.float32)

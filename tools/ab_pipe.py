@@ -47,6 +47,15 @@ CASES = [
     ("4096-pt c128 columns, pipelined", "4096x8192", 0, 1, {"NDFB_PIPE": "1"}),
     ("2048-pt c64 columns, register-resident", "2048x32768", 0, 0, {"NDFB_PIPE": "0"}),
     ("2048-pt c64 columns, pipelined (forced)", "2048x32768", 0, 0, {"NDFB_PIPE": "2"}),
+    ("c2 rows 8192-pt c64, register-resident", "8192x8192", 1, 0, {"NDFB_PIPE": "0"}),
+    ("c2 rows 8192-pt c64, pipelined one-lane tiles", "8192x8192", 1, 0, {"NDFB_PIPE": "2"}),
+    ("4096-pt c128 rows, register-resident", "8192x4096", 1, 1, {"NDFB_PIPE": "0"}),
+    ("4096-pt c128 rows, pipelined one-lane tiles", "8192x4096", 1, 1, {"NDFB_PIPE": "2"}),
+    ("4096-pt c64 rows, register-resident", "16384x4096", 1, 0, {"NDFB_PIPE": "0"}),
+    ("4096-pt c64 rows, pipelined one-lane tiles", "16384x4096", 1, 0, {"NDFB_PIPE": "2"}),
+    ("c5a axis1 1000-pt c128 columns, register-resident", "360x1000x384", 1, 1, {"NDFB_PIPE": "0"}),
+    ("c5a axis1 1000-pt c128 columns, pipelined L=4 (2 CTAs/SM)", "360x1000x384", 1, 1, {"NDFB_PIPE": "2", "NDFB_PIPE_L": "4"}),
+    ("c5a axis1 1000-pt c128 columns, pipelined L=8", "360x1000x384", 1, 1, {"NDFB_PIPE": "2", "NDFB_PIPE_L": "8"}),
 ]
 only = sys.argv[1:] 
 for name, shape, axis, f64, env in CASES:

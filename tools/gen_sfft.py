@@ -284,15 +284,20 @@ def pipe_entries():
     """Software-pipelined persistent column kernels (pipe_kernel.cuh): tiles that own a whole SM (both passes of the 2^24-point
     rows of BASELINE c5b, the long f64 columns), plus a few small schedules for the emulator / GPU parity tests."""
     out = []
-    prod = [(0, 4096, 4), (0, 8192, 2), (0, 2048, 8), (1, 2048, 4), (1, 4096, 2), (1, 1024, 8)]
+    prod = [(0, 4096, 4), (0, 8192, 2), (0, 2048, 8), (1, 2048, 4), (1, 4096, 2), (1, 1024, 8), (1, 1000, 4), (1, 1000, 8)]
     small = [(0, 64, 4), (0, 512, 4), (0, 256, 4), (1, 64, 2), (1, 512, 4), (1, 360, 2)]
-    for f64, N, L in prod + small:
+    # one-lane tiles = contiguous rows in and out (opt-in, NDFB_PIPE=2): 64 KiB rows, two CTAs per SM
+    rows = [(0, 8192, 1), (1, 4096, 1), (0, 4096, 1), (1, 2048, 1), (0, 256, 1), (1, 512, 1)]
+    for f64, N, L in prod + small + rows:
         sc = schedule(N, f64, 1) or schedule(N, f64, 0)
         TL, rad = sc
         rad = list(rad) + [1] * (4 - len(rad))
         R = "double" if f64 else "float"
-        for inmode in (0, 1):
-            out.append(f"    SFFT_PIPE_ENTRY({R}, {f64}, {N}, {TL}, {rad[0]}, {rad[1]}, {rad[2]}, {rad[3]}, {L}, {inmode}, 1),  // T={TL * L}")
+        cs = 16 if f64 else 8
+        for inmode in ((1,) if L == 1 else (0, 1)):
+            smem = L * (N + 4) * cs + L * npad(N, rad[0]) * cs // 2
+            minb = max(1, min((227 * 1024) // smem, 65536 // (TL * L * 64), 4))
+            out.append(f"    SFFT_PIPE_ENTRY({R}, {f64}, {N}, {TL}, {rad[0]}, {rad[1]}, {rad[2]}, {rad[3]}, {L}, {inmode}, {minb}),  // T={TL * L}")
     return out
 
 
