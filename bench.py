@@ -209,18 +209,30 @@ class ConfigBench:
         self.flush_buf.zero_()
 
     def time_call(self, fn, iters=None, flush=False):
+        """Median / minimum device time of one call.  A single call bracketed by two events on an idle GPU also times the host
+        side of the call (Python -> C ABI -> launch, ~7 us: a tenth of a 0.1 ms kernel), so calls shorter than ~0.5 ms are
+        enqueued `reps` times back to back between the events (the arrays are larger than L2; reps = 1 with `flush`)."""
         t = self.torch
         for _ in range(3):
             fn()
         t.cuda.synchronize()
+        reps = 1
+        if not flush:
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            t.cuda.synchronize()
+            reps = max(1, min(8, int(round(0.6 / max(e0.elapsed_time(e1), 1e-3)))))
         ts = []
         for _ in range(iters or self.iters):
             if flush:
                 self.flush()
             e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
             t.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / reps)
         ts.sort()
         return ts[len(ts) // 2], ts[0]
 

@@ -83,8 +83,10 @@ struct ndfb_plan {
     std::mutex mu;
     std::map<std::pair<int, int>, std::unique_ptr<ndfb::Core>> cores;  // (tile kind, n) -> schedule
     // four-step inter-pass twiddles, keyed by total length
-    struct FsTw { void *lo = nullptr, *hi = nullptr; int shift = 0; };
+    struct FsTw { void *lo = nullptr, *hi = nullptr; int shift = 0; long long ntot = 0; };
     std::map<long long, FsTw> fs;
+    // pipelined kernels: W_N^{q NB j2} at [j2 r + q], keyed by (N, first factor, last radix of its schedule)
+    std::map<std::pair<long long, std::pair<int, int>>, void*> fsq;
     // staged Bluestein (lengths with a large prime factor that do not fit one CTA): chirp c[j] and FFT_M(kernel)/M
     struct BigBlu { void *chirp = nullptr, *bhat = nullptr; int M = 0; };
     std::map<long long, BigBlu> bigblu;
@@ -141,12 +143,34 @@ static int get_fs_twiddles(ndfb_plan* p, long long Ntot, ndfb_plan::FsTw* out) {
     for (long long b = 0; b < nhi; ++b) hi[b] = unit_root(shift >= 40 ? 0 : (b << shift), Ntot);
     ndfb_plan::FsTw t;
     t.shift = shift;
+    t.ntot = Ntot;
     int rc;
     if ((rc = dev_set(p->device))) return rc;
     if ((rc = upload_cx<R>(&t.lo, lo))) return rc;
     if ((rc = upload_cx<R>(&t.hi, hi))) return rc;
     p->fs[Ntot] = t;
     *out = t;
+    return 0;
+}
+
+// pipelined kernels: the q-dependent factor of the four-step twiddle, W_N^{q NB j2} for the last radix r of the N1-point
+// schedule (NB = N1 / r) and every lane j2 < nj2, laid out [j2][q] (pipe_kernel.cuh: PipeStore)
+template <typename R>
+static int get_fs_q(ndfb_plan* p, long long Ntot, int N1, int r, long long nj2, void** out) {
+    std::lock_guard<std::mutex> g(p->mu);
+    const auto key = std::make_pair(Ntot, std::make_pair(N1, r));
+    auto it = p->fsq.find(key);
+    if (it != p->fsq.end()) { *out = it->second; return 0; }
+    const long long NB = N1 / r;
+    std::vector<cld> t((size_t)nj2 * r);
+    for (long long j2 = 0; j2 < nj2; ++j2)
+        for (int q = 0; q < r; ++q) t[(size_t)j2 * r + q] = unit_root((long long)(((unsigned long long)q * NB % Ntot) * j2 % Ntot), Ntot);
+    int rc;
+    void* d = nullptr;
+    if ((rc = dev_set(p->device))) return rc;
+    if ((rc = upload_cx<R>(&d, t))) return rc;
+    p->fsq[key] = d;
+    *out = d;
     return 0;
 }
 
@@ -619,6 +643,15 @@ static int try_pipe(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, long 
     a.is_axis = s.is_axis; a.os_axis = s.os_axis; a.conj_in = s.conj_in; a.conj_out = s.conj_out; a.scale = s.scale;
     a.fs_twiddle = s.fs_twiddle; a.fs_dim = s.fs_dim; a.fs_shift = s.fs.shift; a.fs_lo = s.fs.lo; a.fs_hi = s.fs.hi;
     a.ntiles = ntiles;
+    if (s.fs_twiddle) {
+        int rl = pe->r[0];
+        for (int k = 1; k < 4; ++k) if (pe->r[k] > 1) rl = pe->r[k];
+        if (!s.fs.ntot || s.fs_dim < 0 || s.fs_dim >= (int)s.dims.size()) return 0;
+        void* fq = nullptr;
+        int rcq = get_fs_q<R>(p, s.fs.ntot, pe->N, rl, s.dims[s.fs_dim].size, &fq);
+        if (rcq) return rcq;
+        a.fs_q = fq;
+    }
     SfftEntry proxy;
     std::memset((void*)&proxy, 0, sizeof proxy);
     for (int k = 0; k < 4; ++k) proxy.r[k] = pe->r[k];
@@ -1849,6 +1882,7 @@ void ndfb_plan_destroy(ndfb_plan* p) {
         for (auto& kv2 : d.sfft_tw) if (kv2.second) dev_free(kv2.second);
     }
     for (auto& kv : p->fs) { if (kv.second.lo) dev_free(kv.second.lo); if (kv.second.hi) dev_free(kv.second.hi); }
+    for (auto& kv : p->fsq) if (kv.second) dev_free(kv.second);
     for (auto& kv : p->bigblu) { if (kv.second.chirp) dev_free(kv.second.chirp); if (kv.second.bhat) dev_free(kv.second.bhat); }
     delete p;
 }

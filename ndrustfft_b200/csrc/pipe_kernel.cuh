@@ -46,7 +46,8 @@ struct PipeSmem {
     static constexpr int kPitch = INMODE == 0 ? S::N : pitch1();  // elements between lanes (INMODE 1)
     static constexpr size_t kStage = sizeof(Cx<R>) * (INMODE == 0 ? (size_t)L * S::N : (size_t)L * kPitch);
     static constexpr size_t kXch = sizeof(R) * (size_t)L * S::NPAD;
-    static constexpr size_t kTotal = ((kStage + 15) / 16) * 16 + kXch;
+    static constexpr size_t kTotal = ((((kStage + 15) / 16) * 16 + kXch) + 15) / 16 * 16;   // + the lane table (kLaunch)
+    static constexpr size_t kLaunch = kTotal + (size_t)L * 2 * (8 + 8 + 4) + 16;
 };
 
 // twiddles (pass >= 1) and butterflies of pass PASS on the points this thread holds
@@ -64,7 +65,7 @@ NDFB_DEV void pipe_compute(int i, Cx<R> (&v)[S::E], const Cx<R>* __restrict__ tw
                 const int k = KCONST ? k0 : b % P;
                 const Cx<R>* __restrict__ twp = tw + S::twoff(PASS) + k;
 #if NDFB_TW_POW
-                if constexpr (r >= 8 && (r & (r - 1)) == 0 && (S::N & (S::N - 1)) == 0) {
+                if constexpr ((r >= 8 && (r & (r - 1)) == 0 && (S::N & (S::N - 1)) == 0) || (NDFB_TW_POW_ODD && r >= 5)) {
                     Cx<R> t[r];
 #pragma unroll
                     for (int q = 1; q < r; ++q) {
@@ -150,7 +151,7 @@ NDFB_DEV void pipe_passes(const Ctx& c, R* sm, Cx<R> (&v)[S::E], const Cx<R>* __
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
             if ((NB % S::TL) == 0 || b < NB) {
-                auto cur = store.start(b, NB);
+                auto cur = store.start(b, NB, r);
 #pragma unroll
                 for (int q = 0; q < r; ++q) store.next(cur, v[m * r + q]);
             }
@@ -158,25 +159,29 @@ NDFB_DEV void pipe_passes(const Ctx& c, R* sm, Cx<R> (&v)[S::E], const Cx<R>* __
     }
 }
 
-// last-pass store with everything sfft_body's MODE 2 offers except scattered blocks: scale / conjugation, the four-step
-// twiddle from the single table (shift >= 40) or the hi/lo product, strided output
+// last-pass store: scale / conjugation, strided output, and the four-step twiddle W_N^{k j2} of output k = b + q NB of lane j2,
+// factored as W_N^{b j2} (ONE lookup per butterfly: the hi/lo product, or the single table when shift >= 40) times
+// W_N^{q NB j2} = fsq[j2 r + q] (a table of r entries per lane: every thread of a lane reads the same r values, L1 broadcasts).
+// sfft_body's MODE 1 / 2 look every W_N^{k j2} up on its own: 2 scattered table loads per POINT, 11.5 GB of L1 sector traffic
+// for a 2.1 GB pass of the 2^24-point rows of c5b (profiles/round2/r2q_ncu_c5b_nopipe_summary.txt).
 template <typename R>
 struct PipeStore {
     Cx<R>* out; long long os_axis; R sc, sy;
-    int fs_twiddle, fs_shift; const Cx<R>* lo; const Cx<R>* hi; unsigned j2;
-    struct Cur { Cx<R>* p; long long step; unsigned long long e, estep; };
-    NDFB_DEV Cur start(int b, int nb) const {
+    int fs_twiddle, fs_shift; const Cx<R>* lo; const Cx<R>* hi; const Cx<R>* fsq; unsigned j2;
+    struct Cur { Cx<R>* p; long long step; Cx<R> w; const Cx<R>* t; };
+    NDFB_DEV Cur start(int b, int nb, int r) const {
         Cur u; u.p = out + (long long)b * os_axis; u.step = (long long)nb * os_axis;
-        u.e = (unsigned long long)b * j2; u.estep = (unsigned long long)nb * j2;
+        u.w = cmake<R>((R)1, (R)0); u.t = nullptr;
+        if (fs_twiddle) {
+            const unsigned long long e = (unsigned long long)b * j2;
+            u.w = fs_shift >= 40 ? ldg(&lo[(unsigned)e]) : cmul(ldg(&hi[e >> fs_shift]), ldg(&lo[e & ((1ull << fs_shift) - 1)]));
+            u.t = fsq + (size_t)j2 * r;
+        }
         return u;
     }
     NDFB_DEV void next(Cur& u, Cx<R> val) const {
         Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
-        if (fs_twiddle) {
-            if (fs_shift >= 40) y = cmul(y, ldg(&lo[(unsigned)u.e]));
-            else y = cmul(y, cmul(ldg(&hi[u.e >> fs_shift]), ldg(&lo[u.e & ((1ull << fs_shift) - 1)])));
-            u.e += u.estep;
-        }
+        if (fs_twiddle) { y = cmul(y, cmul(u.w, ldg(u.t))); ++u.t; }
         *u.p = y;
         u.p += u.step;
     }
@@ -200,13 +205,21 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_pipe_kernel(const __grid_
     const R sgn_in = a.conj_in ? (R)-1 : (R)1;
     const long long ntiles = a.ntiles;
 
-    // all threads: queue the 16-byte pieces of `tile` (every lane of a launched tile exists: the host checks nlanes % L == 0)
-    auto issue = [&](long long tile) {
+    // lane -> array offsets cost ~25 instructions per batch dim (runtime divisions): computed ONCE per tile and lane by the
+    // first L threads, one tile ahead, and shared through a small double-buffered table behind the exchange buffer
+    struct LaneTab { long long bi[2][L], bo[2][L]; int j2[2][L]; };
+    LaneTab& lt = *reinterpret_cast<LaneTab*>(smem_raw + SM::kTotal);
+    auto fill_lanes = [&](long long tile, int slot) {   // threads < L
+        const LaneBase lb = lane_base(a, tile * L + tid, true, a.fs_dim);
+        lt.bi[slot][tid] = lb.bi; lt.bo[slot][tid] = lb.bo; lt.j2[slot][tid] = lb.j2;
+    };
+    // all threads: queue the 16-byte pieces of the tile whose lane offsets are in `slot` (every lane of a launched tile exists:
+    // the host checks nlanes % L == 0)
+    auto issue = [&](int slot) {
         if constexpr (INMODE == 0) {
             constexpr int CPR = (int)(L * sizeof(Cx<R>) / 16);          // pieces per tile row
             constexpr int TOTAL = N * CPR;
-            const LaneBase lb0 = lane_base(a, tile * L, true, 0);
-            const char* src0 = reinterpret_cast<const char*>(reinterpret_cast<const Cx<R>*>(a.in) + lb0.bi);
+            const char* src0 = reinterpret_cast<const char*>(reinterpret_cast<const Cx<R>*>(a.in) + lt.bi[slot][0]);
             const long long row_bytes = a.is_axis * (long long)sizeof(Cx<R>);
             char* dst0 = reinterpret_cast<char*>(stage);
 #pragma unroll
@@ -218,9 +231,7 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_pipe_kernel(const __grid_
             constexpr int CPL = (int)(N * sizeof(Cx<R>) / 16);          // pieces per lane
 #pragma unroll
             for (int l = 0; l < L; ++l) {
-                // pieces of lane l: p in [l CPL, (l+1) CPL)
-                const LaneBase lbl = lane_base(a, tile * L + l, true, 0);
-                const char* src = reinterpret_cast<const char*>(reinterpret_cast<const Cx<R>*>(a.in) + lbl.bi);
+                const char* src = reinterpret_cast<const char*>(reinterpret_cast<const Cx<R>*>(a.in) + lt.bi[slot][l]);
                 char* dst = reinterpret_cast<char*>(stage + (size_t)l * SM::kPitch);
                 for (int p = tid; p < CPL; p += T) cpasync16(dst + (size_t)p * 16, src + (size_t)p * 16);
             }
@@ -229,8 +240,13 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_pipe_kernel(const __grid_
     };
 
     long long tile = blockIdx.x;
-    if (tile < ntiles) issue(tile);
-    for (; tile < ntiles; tile += gridDim.x) {
+    int slot = 0;
+    if (tile < ntiles && tid < L) fill_lanes(tile, 0);
+    __syncthreads();
+    if (tile < ntiles) issue(0);
+    for (; tile < ntiles; tile += gridDim.x, slot ^= 1) {
+        const bool more = tile + gridDim.x < ntiles;
+        if (more && tid < L) fill_lanes(tile + gridDim.x, slot ^ 1);
         cpasync_wait_all();
         __syncthreads();                         // this tile's input has landed and is visible to every thread
         Cx<R> v[S::E];
@@ -251,12 +267,12 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_pipe_kernel(const __grid_
             }
         }
         __syncthreads();                         // every thread has its points: the staging buffer is free again
-        if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
-        const LaneBase lb = lane_base(a, tile * L + c.l, true, a.fs_dim);
+        if (more) issue(slot ^ 1);
         PipeStore<R> st;
-        st.out = reinterpret_cast<Cx<R>*>(a.out) + lb.bo; st.os_axis = a.os_axis; st.sc = sc; st.sy = a.conj_out ? -sc : sc;
+        st.out = reinterpret_cast<Cx<R>*>(a.out) + lt.bo[slot][c.l]; st.os_axis = a.os_axis; st.sc = sc; st.sy = a.conj_out ? -sc : sc;
         st.fs_twiddle = a.fs_twiddle; st.fs_shift = a.fs_shift;
-        st.lo = reinterpret_cast<const Cx<R>*>(a.fs_lo); st.hi = reinterpret_cast<const Cx<R>*>(a.fs_hi); st.j2 = (unsigned)lb.j2;
+        st.lo = reinterpret_cast<const Cx<R>*>(a.fs_lo); st.hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
+        st.fsq = reinterpret_cast<const Cx<R>*>(a.fs_q); st.j2 = (unsigned)lt.j2[slot][c.l];
         pipe_passes<R, S, L, 0>(c, xch, v, tw, st);
     }
 }

@@ -18,6 +18,9 @@
 #ifndef NDFB_TW_POW
 #define NDFB_TW_POW 1   // +2..10 % on B200 (profiles/r1r_ab_twiddle_powers.jsonl: A = table loads, B = powers)
 #endif
+#ifndef NDFB_TW_POW_ODD
+#define NDFB_TW_POW_ODD 0   // the same for the mixed radices 5..15 (loads W^k, W^2k, W^4k, W^8k; products of depth <= 3): A/B build
+#endif
 
 namespace ndfb {
 
@@ -51,6 +54,7 @@ struct SfftArgs {
                            // in shared memory and send each block with ONE bulk-async copy (cp.async.bulk, the TMA engine)
     const void* fs_lo;
     const void* fs_hi;
+    const void* fs_q;      // pipelined kernels (pipe_kernel.cuh): W_N^{q NB j2} at [j2 r + q], r = last radix, NB = N1 / r
 };
 
 template <int N_, int TL_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
@@ -197,7 +201,7 @@ struct SfftPass {
                 if (!FIRST) {
                     const Cx<R>* __restrict__ twp = KCONST ? twp0 : tw + S::twoff(PASS) + k;
 #if NDFB_TW_POW
-                    if constexpr (r >= 8 && (r & (r - 1)) == 0 && (S::N & (S::N - 1)) == 0) {
+                    if constexpr ((r >= 8 && (r & (r - 1)) == 0 && (S::N & (S::N - 1)) == 0) || (NDFB_TW_POW_ODD && r >= 5)) {
                         // load W^k, W^2k, W^4k, W^8k and form the other powers as products (depth <= 3): 4 table loads, not 15
                         Cx<R> t[r];
 #pragma unroll

@@ -696,6 +696,11 @@ def test_pipelined_column_kernel_four_step(hs, capfd):
         hs.run("ndifft", 64 * 512, (1, 64 * 512), 1, np.float64, seed=8)
         err = capfd.readouterr().err
         assert err.count("in=lane-adjacent") == 2 and err.count("in=rows") == 2, err
+        # beyond 2^17 points the four-step twiddle base is the hi/lo table product (times the per-lane factor table)
+        os.environ["NDFB_FS_N1"] = "512"
+        hs.run("ndfft", 512 * 512, (1, 512 * 512), 1, np.float32, seed=9)
+        err = capfd.readouterr().err
+        assert err.count("in=lane-adjacent") == 1 and err.count("in=rows") == 1, err
     finally:
         for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1"):
             os.environ.pop(k, None)

@@ -39,6 +39,10 @@ CASES = [  # name, fn, in shape, out shape, axis, dtype, n, handler
     ("c4 dct2 cols", "nddct2", (4096, 4096), None, 0, np.float64, 4096, "DctHandler"),
     ("c4 dct1 rows", "nddct1", (4096, 4096), None, 1, np.float64, 4096, "DctHandler"),
     ("c4 dct4 rows", "nddct4", (4096, 4096), None, 1, np.float64, 4096, "DctHandler"),
+    ("c4 dct1 cols", "nddct1", (4096, 4096), None, 0, np.float64, 4096, "DctHandler"),
+    ("ramp 264 c128 axis0", "ndfft", (264, 264 * 64), None, 0, np.float64, 264, "FftHandler"),
+    ("rows 729 f32", "ndfft", (65536, 729), None, 1, np.float32, 729, "FftHandler"),
+    ("rows 600 f64", "ndfft", (65536, 600), None, 1, np.float64, 600, "FftHandler"),
     ("c5a 360 axis0", "ndfft", (360, 1000, 384), None, 0, np.float64, 360, "FftHandler"),
     ("c5a 1000 axis1", "ndfft", (360, 1000, 384), None, 1, np.float64, 1000, "FftHandler"),
     ("c5a 384 axis2", "ndfft", (360, 1000, 384), None, 2, np.float64, 384, "FftHandler"),
@@ -73,7 +77,9 @@ def main():
             row[tag + "_ms"] = round(ms, 4)
             row[tag + "_frac"] = round(nbytes / (ms * 1e-3) / 1e9 / PEAK, 3)
             if ref is None: ref = y.clone()
-            else: row["identical"] = bool(torch.equal(ref, y))
+            else:
+                row["identical"] = bool(torch.equal(ref, y))
+                row["rel_l2_B_vs_A"] = float(torch.linalg.vector_norm((y - ref).flatten()) / torch.linalg.vector_norm(ref.flatten()))
         row["B/A"] = round(row["B_ms"] / row["A_ms"], 3)
         print(json.dumps(row), flush=True)
         del x, y, ref

@@ -36,6 +36,7 @@ print(json.dumps({"variant": os.environ.get("VARIANT"), "shape": os.environ["SHA
 CASES = [
     ("c5b two-pass, register-resident", "64x16777216", 1, 0, {"NDFB_PIPE": "0"}),
     ("c5b two-pass, pipelined", "64x16777216", 1, 0, {"NDFB_PIPE": "1"}),
+    ("c5b two-pass, pipelined, two-lane tiles (2 CTAs/SM, 16-byte rows)", "64x16777216", 1, 0, {"NDFB_PIPE": "2", "NDFB_PIPE_L": "2"}),
     ("c2 axis0 two passes (default)", "8192x8192", 0, 0, {"NDFB_PIPE": "0"}),
     ("c2 axis0 ONE pass, 16-byte rows, register-resident", "8192x8192", 0, 0, {"NDFB_PIPE": "0", "NDFB_STRIDED_FOURSTEP": "0"}),
     ("c2 axis0 ONE pass, 16-byte rows, pipelined", "8192x8192", 0, 0, {"NDFB_PIPE": "1", "NDFB_STRIDED_FOURSTEP": "0"}),

@@ -284,7 +284,7 @@ def pipe_entries():
     """Software-pipelined persistent column kernels (pipe_kernel.cuh): tiles that own a whole SM (both passes of the 2^24-point
     rows of BASELINE c5b, the long f64 columns), plus a few small schedules for the emulator / GPU parity tests."""
     out = []
-    prod = [(0, 4096, 4), (0, 8192, 2), (0, 2048, 8), (1, 2048, 4), (1, 4096, 2), (1, 1024, 8), (1, 1000, 4), (1, 1000, 8)]
+    prod = [(0, 4096, 4), (0, 8192, 2), (0, 2048, 8), (1, 2048, 4), (1, 4096, 2), (1, 1024, 8), (1, 1000, 4), (1, 1000, 8), (0, 4096, 2)]
     small = [(0, 64, 4), (0, 512, 4), (0, 256, 4), (1, 64, 2), (1, 512, 4), (1, 360, 2)]
     # one-lane tiles = contiguous rows in and out (opt-in, NDFB_PIPE=2): 64 KiB rows, two CTAs per SM
     rows = [(0, 8192, 1), (1, 4096, 1), (0, 4096, 1), (1, 2048, 1), (0, 256, 1), (1, 512, 1)]
