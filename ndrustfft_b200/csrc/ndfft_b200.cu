@@ -593,12 +593,15 @@ static int rows_bulk_enabled() {   // 0 off, 1 on for batches that fill the GPU,
     return e ? atoi(e) : 0;
 }
 
-// Software-pipelined persistent column kernel (pipe_kernel.cuh) for tiles that own a whole SM: NDFB_PIPE=0 off, 1 (default) where
+// Software-pipelined persistent column kernel (pipe_kernel.cuh) for tiles that own a whole SM: NDFB_PIPE=0 (default) off, 1 where
 // the register-resident kernel would run one CTA per SM and the batch gives every SM several tiles, 2 wherever an instance exists
-// (tests).  *done = 1 when it has launched.
+// (tests).  *done = 1 when it has launched.  Measured on B200 (profiles/round2/r2r_ab_pipe.jsonl): bit-identical results, the same
+// speed within +-6 % (c5b 11.28 vs 11.30 ms; 2048-point c128 columns 0.337 vs 0.359 ms; 4096-point c64 columns 0.448 vs 0.421 ms),
+// so the register-resident kernels stay the default: what bounds these tiles is the barrier-separated phases of the ONE CTA an
+// SM can hold (a 128 KB tile is half the register file), not exposed load latency.
 static int pipe_mode() {
     const char* e = std::getenv("NDFB_PIPE");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
 }
 template <typename R>
 static int try_pipe(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, long long nlanes, stream_t stream, int* done) {
@@ -863,6 +866,14 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             a.is_axis = s.is_axis; a.os_axis = s.os_axis;
             a.n = t.n; a.scale = s.scale;
             a.tabA = s.core->d.tabA; a.tabB = s.core->d.tabB;
+            // contiguous DCT-III / DCT-IV output rows that start on 2-real boundaries: mirror-paired last pass, pairs of reals stored
+            // straight from registers (sfft_kernel.cuh: kMirrorOut); NDFB_NO_MIRROR_OUT keeps the staged copy-out (A/B runs)
+            if (!cols && s.os_axis == 1 && (rk == RK_DCT3 || rk == RK_DCT4) && !std::getenv("NDFB_NO_MIRROR_OUT")) {
+                bool al = ((uintptr_t)s.out % (2 * sizeof(R))) == 0;
+                for (auto& d : s.dims) if (d.os % 2) al = false;
+                a.vec_out = al ? 1 : 0;
+                if (a.vec_out && trace) fprintf(stderr, "[ndfb] rsfft kind=%d rows: mirror-paired output pass where the schedule allows it (aligned contiguous rows)\n", rk);
+            }
             SfftEntry proxy;
             std::memset(&proxy, 0, sizeof proxy);
             for (int i = 0; i < 4; ++i) proxy.r[i] = e->r[i];

@@ -19,7 +19,9 @@
 #define NDFB_TW_POW 1   // +2..10 % on B200 (profiles/r1r_ab_twiddle_powers.jsonl: A = table loads, B = powers)
 #endif
 #ifndef NDFB_TW_POW_ODD
-#define NDFB_TW_POW_ODD 0   // the same for the mixed radices 5..15 (loads W^k, W^2k, W^4k, W^8k; products of depth <= 3): A/B build
+#define NDFB_TW_POW_ODD 1   // the same for the mixed radices 5..15 (loads W^k, W^2k, W^4k, W^8k; products of depth <= 3): 384-point c128 rows
+                            // +7 %, 360-point columns +2 %, the 4095-point DCT-I core +2-3 %, neutral elsewhere, same accuracy
+                            // (profiles/round2/r2r_ab_tw_pow_odd.jsonl: A = table loads, B = powers)
 #endif
 
 namespace ndfb {
@@ -284,6 +286,14 @@ constexpr bool kMirrorEpi = S::NP >= 2 && S::G(S::NP - 1) % 2 == 0 && S::nbf(S::
 template <class S>
 constexpr bool kShuffleEpi = NDFB_SHUFFLE_EPI && S::NP >= 2 && S::G(S::NP - 1) == 1 && S::nbf(S::NP - 1) == S::TL && S::TL % 32 == 0 &&
                              S::radix(S::NP - 1) % 2 == 0;
+
+// Mirror-paired last pass for the kinds whose OUTPUT rows interleave bins k and N-1-k (DCT-III: inverse Makhoul order, DCT-IV:
+// out[2k] / out[n-1-2k]): thread i takes butterflies p and NB-1-p, whose outputs k = p + q NB and N-1-k = (NB-1-p) + (r-1-q) NB are
+// each other's mirror, and writes whole aligned 16 / 32-byte pieces of the contiguous output row straight from registers: the
+// staging copy through shared memory (one write + one read of the lane, a barrier) disappears.  No self-paired butterflies.
+template <class S>
+constexpr bool kMirrorOut = S::NP >= 2 && S::G(S::NP - 1) % 2 == 0 && S::nbf(S::NP - 1) == S::G(S::NP - 1) * S::TL &&
+                            S::nbf(S::NP - 1) % 2 == 0 && S::radix(S::NP - 1) % 2 == 0;
 
 // The same pairing on the FIRST pass for the kinds whose inputs come in mirror pairs (C2R, DCT-III: slots j and N-j are built
 // from the same two spectrum bins): schedules that START with the small radix (4.8.8.8) give pass 0 two butterflies per thread.
@@ -894,10 +904,12 @@ struct RsfftArgs {
     long long done_group;
     const void* tabA; // exp(-2 pi i k / (2N)), k <= N   (DCT-IV: exp(-i pi j / n))
     const void* tabB; // DCT-II/III: exp(-i pi k / (2n));  DCT-IV: exp(-i pi (4j+1) / (4n))
+    int vec_out;      // contiguous output rows start on 2-real boundaries: DCT-III / DCT-IV may store pairs of reals (kMirrorOut)
 };
 
 // UNIT: contiguous rows on both sides (axis strides 1): address arithmetic folds to constants
-template <typename R, class S, int L, bool COLS, int KIND, bool UNIT>
+// VEC: (UNIT rows) output rows are aligned for 2-real vector stores: DCT-III / DCT-IV run the mirror-paired last pass (kMirrorOut)
+template <typename R, class S, int L, bool COLS, int KIND, bool UNIT, bool VEC = false>
 NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     constexpr int N = S::N;
     constexpr int n = KIND == RK_DCT1 ? N + 1 : 2 * N;   // logical real length (== a.n; the host only launches matching plans)
@@ -905,7 +917,8 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
     constexpr bool OUT_CX = KIND == RK_R2C;
     // which sides need the coalesced staging copy when the lane is a contiguous row
     constexpr bool STAGE_IN = !COLS && (KIND == RK_DCT2 || KIND == RK_DCT4);
-    constexpr bool STAGE_OUT = !COLS && (KIND == RK_DCT3 || KIND == RK_DCT4);
+    constexpr bool MIRROR_OUT = VEC && UNIT && !COLS && (KIND == RK_DCT3 || KIND == RK_DCT4) && kMirrorOut<S>;
+    constexpr bool STAGE_OUT = !COLS && (KIND == RK_DCT3 || KIND == RK_DCT4) && !MIRROR_OUT;
     constexpr bool PAIR_EPI = KIND == RK_R2C || KIND == RK_DCT1 || KIND == RK_DCT2;   // outputs need Z[k] and Z[N-k]
     NDFB_DYN_SMEM(smem_raw);
     SfftCtx<R, S, L, COLS> c;
@@ -1159,6 +1172,55 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
         if (b == 0) emit(0, v[0], v[0], true);        // also bin N (bin 0 is written twice with the same value)
         return;
     }
+    if constexpr (MIRROR_OUT && !MIRROR_PRO) {
+        constexpr int LP = S::NP - 1, r = S::radix(LP), P = S::before(LP), NB = S::nbf(LP), HG = S::G(LP) / 2;
+        SfftUntil<R, S, L, COLS, 0, LP, STAGE_IN || PAIR_PRO>::run(c, v, tw, load, store);
+#pragma unroll
+        for (int m = 0; m < HG; ++m) {
+            const int b0 = c.i + S::TL * m, b1 = NB - 1 - b0;
+            Cx<R>* u = &v[2 * m * r];
+#pragma unroll
+            for (int q = 0; q < r; ++q) {
+                u[q] = c.smem[c.addr(b0 + q * NB)];
+                u[r + q] = c.smem[c.addr(b1 + q * NB)];
+            }
+            const Cx<R>* __restrict__ t0 = tw + S::twoff(LP) + (b0 % P);
+            const Cx<R>* __restrict__ t1 = tw + S::twoff(LP) + (b1 % P);
+#pragma unroll
+            for (int q = 1; q < r; ++q) {
+                u[q] = cmul(u[q], ldg(&t0[(q - 1) * P]));
+                u[r + q] = cmul(u[r + q], ldg(&t1[(q - 1) * P]));
+            }
+            Dft<R, r>::run(&u[0]);
+            Dft<R, r>::run(&u[r]);
+        }
+        if (!valid) return;
+        auto put2 = [&](int t, R x0, R x1) { *reinterpret_cast<Cx<R>*>(out_r + t) = cmake<R>(x0, x1); };   // t even: aligned pair
+#pragma unroll
+        for (int m = 0; m < HG; ++m) {
+            const int b0 = c.i + S::TL * m;
+            const Cx<R>* u = &v[2 * m * r];
+#pragma unroll
+            for (int q = 0; q < r; ++q) {
+                const int k = b0 + q * NB;                    // its mirror N-1-k is output r-1-q of butterfly NB-1-b0
+                const Cx<R> yk = u[q], ym = u[r + (r - 1 - q)];
+                if (KIND == RK_DCT3) {
+                    // x[4 lo .. 4 lo + 3] = h (Re y_lo, -Im y_hi, -Im y_lo, Re y_hi), lo = min(k, N-1-k)  (k < N/2 <=> q < r/2)
+                    const R h = (R)0.5 * sc;
+                    const bool klo = q < r / 2;
+                    const Cx<R> ylo = klo ? yk : ym, yhi = klo ? ym : yk;
+                    const int t = 4 * (klo ? k : N - 1 - k);
+                    put2(t, h * ylo.x, -h * yhi.y);
+                    put2(t + 2, -h * ylo.y, h * yhi.x);
+                } else {
+                    const Cx<R> Ck = cmul(yk, ldg(&tabB[k])), Cm = cmul(ym, ldg(&tabB[N - 1 - k]));
+                    put2(2 * k, sc * Ck.x, -sc * Cm.y);                  // out[2k], out[2k+1] = out[n-1-2k']
+                    put2(n - 2 - 2 * k, sc * Cm.x, -sc * Ck.y);          // out[2k'] = out[n-2-2k], out[n-1-2k]
+                }
+            }
+        }
+        return;
+    }
     if constexpr (MIRROR_PRO) {
         // pass 0 with butterflies i and NB - i in one thread: the zip of bins j and N - j feeds both, straight from global memory
         constexpr int r = S::R0, NB = S::nbf(0);
@@ -1276,7 +1338,12 @@ NDFB_DEV void rsfft_signal(const RsfftArgs& a, int L) {
 template <typename R, class S, int L, bool COLS, int KIND, int MINB>
 __global__ void __launch_bounds__(S::TL* L, MINB) rsfft_kernel(const __grid_constant__ RsfftArgs a) {
     if constexpr (!COLS) {
-        if (a.is_axis == 1 && a.os_axis == 1) { rsfft_body<R, S, L, COLS, KIND, true>(a); rsfft_signal(a, L); return; }
+        if (a.is_axis == 1 && a.os_axis == 1) {
+            if constexpr ((KIND == RK_DCT3 || KIND == RK_DCT4) && kMirrorOut<S>) {
+                if (a.vec_out) { rsfft_body<R, S, L, COLS, KIND, true, true>(a); rsfft_signal(a, L); return; }
+            }
+            rsfft_body<R, S, L, COLS, KIND, true>(a); rsfft_signal(a, L); return;
+        }
     }
     rsfft_body<R, S, L, COLS, KIND, false>(a);
     rsfft_signal(a, L);

@@ -704,3 +704,19 @@ def test_pipelined_column_kernel_four_step(hs, capfd):
     finally:
         for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1"):
             os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("op,n,rd", [("nddct3", 4096, np.float64), ("nddct4", 4096, np.float64), ("nddct3", 2048, np.float64), ("nddct4", 2048, np.float64),
+                                     ("nddct3", 4096, np.float32), ("nddct4", 4096, np.float32), ("nddct4", 512, np.float64), ("nddct3", 1024, np.float32)])
+def test_mirror_paired_output_pass(hs, op, n, rd, capfd):
+    """DCT-III / DCT-IV on contiguous aligned rows: schedules whose last pass has an even number of butterflies per thread (8.8.8.4,
+    8.8.8.2, 16.16.8, 8.8.4, 16.16.2) pair butterflies p and NB-1-p and store pairs of reals straight from registers.  Ragged tiles,
+    default and no normalisation.  (Rows that start on an odd element keep the staged copy-out: GPU test, device views.)"""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run(op, n, (3, n), 1, rd, seed=n)
+        assert "mirror-paired output" in capfd.readouterr().err
+        hs.run(op, n, (5, n), 1, rd, seed=n + 1, norm="none")
+    finally:
+        del os.environ["NDFB_TRACE"]

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Same-box A/B of library code paths selected by environment variables (one subprocess per variant):
+   python tools/ab_env.py [substring filters...]   ->  one JSON line per (case, variant)."""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODE = r'''
+import sys, json, os
+sys.path.insert(0, %r)
+import numpy as np, torch, ndrustfft_b200 as nb
+from oracle import ndrustfft_oracle as orc
+shape = tuple(int(v) for v in os.environ["SHAPE"].split("x")); axis = int(os.environ["AXIS"]); f64 = os.environ["F64"] == "1"; op = os.environ["OP"]
+rt = torch.float64 if f64 else torch.float32
+rd = np.float64 if f64 else np.float32
+n = shape[axis]
+cx = op in ("ndfft", "ndifft")
+x = torch.complex(torch.rand(shape, device="cuda", dtype=rt) * 2 - 1, torch.rand(shape, device="cuda", dtype=rt) * 2 - 1) if cx else torch.rand(shape, device="cuda", dtype=rt) * 2 - 1
+y = torch.empty_like(x)
+h = (nb.FftHandler if cx else nb.DctHandler)(n, rd)
+f = getattr(nb, op)
+for _ in range(3): f(x, y, h, axis)
+torch.cuda.synchronize()
+reps = int(os.environ.get("REPS", "4"))
+ts = []
+for _ in range(10):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): f(x, y, h, axis)
+    e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / reps)
+ts.sort()
+idx = [slice(None)] * len(shape)
+for d in range(len(shape)):
+    if d != axis: idx[d] = slice(0, 3)
+xs = x[tuple(idx)].cpu().numpy(); ys = y[tuple(idx)].cpu().numpy()
+ho = (orc.FftHandler if cx else orc.DctHandler)(n)
+want = np.zeros(xs.shape, np.complex128 if cx else np.float64)
+getattr(orc, op)(xs.astype(np.complex128 if cx else np.float64), want, ho, axis)
+ms = ts[len(ts) // 2]
+nbytes = 2 * x.numel() * x.element_size()
+print(json.dumps({"case": os.environ["CASE"], "variant": os.environ["VARIANT"], "ms": round(ms, 4), "ms_min": round(ts[0], 4),
+                  "frac": round(nbytes / (ms * 1e-3) / 1e9 / 6547.8, 4), "rel_l2": orc.rel_l2(ys, want)}))
+''' % ROOT
+CASES = [  # case, op, shape, axis, f64, [(variant, env)]
+    ("c4 nddct3 rows 4096^2 f64", "nddct3", "4096x4096", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
+    ("c4 nddct4 rows 4096^2 f64", "nddct4", "4096x4096", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
+    ("nddct3 rows 8192x4096 f32", "nddct3", "8192x4096", 1, 0, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
+    ("nddct4 rows 16384x2048 f64", "nddct4", "16384x2048", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
+    ("nddct3 rows 32768x1024 f64", "nddct3", "32768x1024", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
+]
+only = sys.argv[1:]
+for case, op, shape, axis, f64, variants in CASES:
+    if only and not any(o in case for o in only):
+        continue
+    for vname, env in variants:
+        e = dict(os.environ); e.update(env); e.update({"CASE": case, "VARIANT": vname, "SHAPE": shape, "AXIS": str(axis), "F64": str(f64), "OP": op})
+        p = subprocess.run([sys.executable, "-c", CODE], env=e, capture_output=True, text=True)
+        line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        print(line[0] if line else json.dumps({"case": case, "variant": vname, "error": p.stderr[-400:]}), flush=True)
