@@ -206,7 +206,7 @@ inline bool jit_radices(int N, bool f64, int out[4], int* npass, int* TL_out) {
     return true;
 }
 
-inline int jit_npad(int N, int r0) { return N + N / r0; }
+inline int jit_npad(int N, int r0) { return (r0 % 2) ? N : N + N / r0; }   // Sched::NPAD
 
 inline bool jit_plan(int N, bool f64, bool cols, bool real_kind, long long nlanes, JitSched* s) {
     if (N < 4) return false;

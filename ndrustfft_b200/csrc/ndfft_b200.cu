@@ -868,11 +868,15 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             a.tabA = s.core->d.tabA; a.tabB = s.core->d.tabB;
             // contiguous DCT-III / DCT-IV output rows that start on 2-real boundaries: mirror-paired last pass, pairs of reals stored
             // straight from registers (sfft_kernel.cuh: kMirrorOut); NDFB_NO_MIRROR_OUT keeps the staged copy-out (A/B runs)
-            if (!cols && s.os_axis == 1 && (rk == RK_DCT3 || rk == RK_DCT4) && !std::getenv("NDFB_NO_MIRROR_OUT")) {
+            // Measured on B200 (profiles/round2/r2s_ab_mirror_out.jsonl): DCT-IV +10-11 % (4096^2 f64 rows 0.084 -> 0.076 ms), DCT-III f32 +7 %,
+            // DCT-III f64 -3 % (its zip prologue already fills the shared-memory pipe): f64 DCT-III keeps the staged copy-out
+            // unless NDFB_MIRROR_OUT=1 asks for it.
+            const bool want_mirror = rk == RK_DCT4 || (rk == RK_DCT3 && (sizeof(R) == 4 || std::getenv("NDFB_MIRROR_OUT")));
+            if (!cols && s.os_axis == 1 && want_mirror && !std::getenv("NDFB_NO_MIRROR_OUT")) {
                 bool al = ((uintptr_t)s.out % (2 * sizeof(R))) == 0;
                 for (auto& d : s.dims) if (d.os % 2) al = false;
                 a.vec_out = al ? 1 : 0;
-                if (a.vec_out && trace) fprintf(stderr, "[ndfb] rsfft kind=%d rows: mirror-paired output pass where the schedule allows it (aligned contiguous rows)\n", rk);
+                if (a.vec_out && trace) fprintf(stderr, "[ndfb] real kind=%d rows: mirror-paired output pass where the schedule allows it (aligned contiguous rows)\n", rk);
             }
             SfftEntry proxy;
             std::memset(&proxy, 0, sizeof proxy);

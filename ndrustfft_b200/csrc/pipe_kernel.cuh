@@ -98,10 +98,10 @@ struct PipeExchange {
     template <class Ctx>
     static NDFB_DEV void run(const Ctx& c, R* __restrict__ sm, Cx<R> (&v)[S::E]) {
         const int k0 = c.i % Pw;
-        const int wbase = !FW ? 0 : (PASS == 0 ? c.slot_of(c.i * (S::R0 + 1)) : c.slot_of(S::pad((c.i - k0) * rw + k0)));
+        const int wbase = !FW ? 0 : (PASS == 0 ? c.slot_of(c.i * S::R0P) : c.slot_of(S::pad((c.i - k0) * rw + k0)));
         const int rbase = FR ? c.slot_of(S::pad(c.i)) : 0;
         auto waddr = [&](int m, int q) -> int {
-            if (FW) return wbase + (PASS == 0 ? (S::TL * m * (S::R0 + 1) + q) : S::pad(S::TL * m * rw + q * Pw)) * c.kscale;
+            if (FW) return wbase + (PASS == 0 ? (S::TL * m * S::R0P + q) : S::pad(S::TL * m * rw + q * Pw)) * c.kscale;
             const int b = c.i + S::TL * m;
             const int k = KCONST ? k0 : b % Pw;
             return c.addr((b - k) * rw + k + q * Pw);

@@ -79,15 +79,19 @@ struct Sched {
     static constexpr int twoff(int p) { return p <= 1 ? 0 : twoff(p - 1) + twsize(p - 1); }
     static constexpr int TWTOTAL = twsize(1) + twsize(2) + twsize(3);
     static constexpr int E = cmax(cmax(EP(0), EP(1)), cmax(EP(2), EP(3)));      // register slots per thread
-    // one pad element per R0 points keeps the stride-R0 writes of pass 0 off a single bank
-    static constexpr int pad(int a) { return a + a / R0_; }
-    static constexpr int NPAD = N_ + N_ / R0_;
+    // one pad element per R0 points keeps the stride-R0 writes of pass 0 off a single bank.  An ODD first radix needs none: its
+    // stride is already odd, and the pad made it even (13.9.7.5, the 4095-point DCT-I core of c4: 1.60 wavefronts per ideal one
+    // with the pad, 1.01 without; 9.9.9: 1.77 -> 1.00; bank model of every exchange in tools/bank_model.py)
+    static constexpr bool PADDED = (R0_ % 2) == 0;
+    static constexpr int pad(int a) { return PADDED ? a + a / R0_ : a; }
+    static constexpr int NPAD = PADDED ? N_ + N_ / R0_ : N_;
+    static constexpr int R0P = PADDED ? R0_ + 1 : R0_;   // padded distance of consecutive pass-0 butterflies
     // Address fast paths: when the per-thread part and the compile-time part of an index are each multiples of R0
     // where it matters, pad(thread + const) = pad(thread) + pad(const) and every shared-memory access becomes
-    // "one precomputed register + immediate offset".
-    static constexpr bool fast_read(int p) { return p >= 1 && p < NP && TL_ % R0_ == 0 && nbf(p) % R0_ == 0; }
+    // "one precomputed register + immediate offset" (without padding the positions are additive as they are).
+    static constexpr bool fast_read(int p) { return p >= 1 && p < NP && (!PADDED || (TL_ % R0_ == 0 && nbf(p) % R0_ == 0)); }
     static constexpr bool fast_write(int p) {
-        return p == 0 ? true : (p < NP - 1 && TL_ % before(p) == 0 && before(p) % R0_ == 0);
+        return p == 0 ? true : (p < NP - 1 && TL_ % before(p) == 0 && (!PADDED || before(p) % R0_ == 0));
     }
 };
 
@@ -193,8 +197,8 @@ struct SfftPass {
         if ((!FIRST && !LAST) || (FIRST && SYNC0 && !LAST) || (LAST && SYNCL)) __syncthreads();
         const int k0 = c.i % P;
         const Cx<R>* __restrict__ twp0 = tw + S::twoff(PASS) + k0;
-        // write base for the fast paths:  pass 0: b (R0 + 1);  later passes: pad((i - k) r + k)
-        const int wbase = !FW ? 0 : (FIRST ? c.slot_of(c.i * (S::R0 + 1)) : c.slot_of(S::pad((c.i - k0) * r + k0)));
+        // write base for the fast paths:  pass 0: b R0P (= R0 + 1 when padded);  later passes: pad((i - k) r + k)
+        const int wbase = !FW ? 0 : (FIRST ? c.slot_of(c.i * S::R0P) : c.slot_of(S::pad((c.i - k0) * r + k0)));
 #pragma unroll
         for (int m = 0; m < G; ++m) {
             const int b = c.i + S::TL * m;
@@ -231,8 +235,8 @@ struct SfftPass {
                 } else if (FW) {
 #pragma unroll
                     for (int q = 0; q < r; ++q) {
-                        // pass 0: pad(b r + q) = b (r + 1) + q;  later: pad(thread part) + pad(TL m r + q P)
-                        const int cpart = FIRST ? (S::TL * m * (S::R0 + 1) + q) : S::pad(S::TL * m * r + q * P);
+                        // pass 0: pad(b r + q) = b R0P + q;  later: pad(thread part) + pad(TL m r + q P)
+                        const int cpart = FIRST ? (S::TL * m * S::R0P + q) : S::pad(S::TL * m * r + q * P);
                         c.smem[wbase + cpart * c.kscale] = v[m * r + q];
                     }
                 } else {

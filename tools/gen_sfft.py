@@ -64,7 +64,7 @@ def schedule(N, f64, fam):
 
 
 def npad(N, r0):
-    return N + N // r0
+    return N if r0 % 2 else N + N // r0       # Sched::NPAD: an odd first radix needs no pad
 
 
 def make(f64, N, TL, rad, L, cols, fam, minb=None, always_smem=False):
