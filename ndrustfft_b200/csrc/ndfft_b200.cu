@@ -174,6 +174,26 @@ static int get_fs_q(ndfb_plan* p, long long Ntot, int N1, int r, long long nj2, 
     return 0;
 }
 
+// column kernels: the lane-dependent factor of the four-step twiddle, W_N^{k l} for output index k < N1 and lane l < L of a
+// tile, laid out [k][l] (sfft_kernel.cuh: SfftGStore MODE 4); keyed like the pipelined kernels' table with -L as third key
+template <typename R>
+static int get_fs_kl(ndfb_plan* p, long long Ntot, int N1, int L, void** out) {
+    std::lock_guard<std::mutex> g(p->mu);
+    const auto key = std::make_pair(Ntot, std::make_pair(N1, -L));
+    auto it = p->fsq.find(key);
+    if (it != p->fsq.end()) { *out = it->second; return 0; }
+    std::vector<cld> t((size_t)N1 * L);
+    for (long long k = 0; k < N1; ++k)
+        for (int l = 0; l < L; ++l) t[(size_t)k * L + l] = unit_root(k * l % Ntot, Ntot);
+    int rc;
+    void* d = nullptr;
+    if ((rc = dev_set(p->device))) return rc;
+    if ((rc = upload_cx<R>(&d, t))) return rc;
+    p->fsq[key] = d;
+    *out = d;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // workspaces (per host thread)
 // ------------------------------------------------------------------------------------------------------
@@ -534,6 +554,16 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     a.nblk_ptr = s.nblk_ptr;
     for (int i = 0; i < 8; ++i) a.blk_ptr[i] = s.blk_ptr[i];
     a.trans_store = trans_next ? 1 : 0;
+    // Column tiles whose lanes are consecutive j2 (the lane dim IS the twiddle dim and holds whole tiles): the four-step twiddle is
+    // formed as (tile-uniform hi/lo lookup) x (coalesced [k][l] table) instead of one scattered lookup per point (MODE 4).
+    if (s.fs_twiddle && e->cols && s.fs_dim == 0 && !s.os_blk && !s.nblk_ptr && !s.dims.empty() && s.dims[0].size % e->L == 0 && s.fs.ntot &&
+        !std::getenv("NDFB_NO_FS_FACTORED")) {
+        void* tq = nullptr;
+        int rc = get_fs_kl<R>(p, s.fs.ntot, e->N, e->L, &tq);
+        if (rc) return rc;
+        a.fs_q = tq;
+        if (std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] four-step twiddle factored: tile-uniform lookup x [k][l] table (%d x %d)\n", e->N, e->L);
+    }
     // long contiguous rows: every CTA asks the L2 for the row that will be started when it retires (NDFB_L2_PREFETCH=<waves>, 0 = off)
     // Measured on B200 (tools/ab_l2_prefetch.py, profiles/round2/r2k_ab_l2_prefetch.jsonl): half a wave ahead gains 2-4 % on 32-64 KiB
     // rows (8192-point c64: 0.255 -> 0.245 ms), one or two waves ahead lose (the lines are evicted or fight the demand loads).

@@ -56,7 +56,8 @@ struct SfftArgs {
                            // in shared memory and send each block with ONE bulk-async copy (cp.async.bulk, the TMA engine)
     const void* fs_lo;
     const void* fs_hi;
-    const void* fs_q;      // pipelined kernels (pipe_kernel.cuh): W_N^{q NB j2} at [j2 r + q], r = last radix, NB = N1 / r
+    const void* fs_q;      // column kernels, four-step twiddle factored (SfftGStore MODE 4): W_N^{k l} at [k L + l], k < N1, l < L;
+                           // pipelined kernels (pipe_kernel.cuh): W_N^{q NB j2} at [j2 r + q], r = last radix, NB = N1 / r
 };
 
 template <int N_, int TL_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
@@ -138,19 +139,36 @@ struct SfftGLoad {
         return x;
     }
 };
+// MODE 4: the four-step twiddle W_N^{k j2} of lane j2 = j20 + l (tile base + lane within the tile) factored as
+// W_N^{k j20} (index the same for every lane of the tile: warp-uniform hi / lo lookups) x W_N^{k l} (a plan-owned table [k][l] of
+// N1 x L entries, read coalesced across the lanes, L1-resident).  MODE 1 / 2 look W_N^{k j2} up per point with a per-lane index:
+// 32 different table lines per warp request (the column passes of the 2^24-point rows of c5b: 4.4-4.6 ms per pass against 2.7 ms
+// for the pass without a twiddle; profiles/round2/r2u_c5b_launches_*.csv).
 template <typename R, int MODE>
 struct SfftGStore {
     static constexpr bool kStrided = true;
     Cx<R>* out; long long os_axis; R sc, sy; bool valid; const Cx<R>* fs; unsigned j2;
-    struct Cur { Cx<R>* p; long long step; const Cx<R>* t; unsigned tstep; };
+    const Cx<R>* hi; const Cx<R>* tq; int shift; unsigned j20; int lane, tl;   // MODE 4
+    struct Cur { Cx<R>* p; long long step; const Cx<R>* t; unsigned tstep; unsigned long long e, estep; };
     NDFB_DEV Cur start(int b, int nb) const {
         Cur u; u.p = out + (long long)b * os_axis; u.step = (long long)nb * os_axis;
-        u.t = fs + (unsigned)b * j2; u.tstep = (unsigned)nb * j2;
+        if (MODE == 4) {
+            u.t = tq + (unsigned)b * (unsigned)tl + (unsigned)lane; u.tstep = (unsigned)nb * (unsigned)tl;
+            u.e = (unsigned long long)b * j20; u.estep = (unsigned long long)nb * j20;
+        } else {
+            u.t = fs + (unsigned)b * j2; u.tstep = (unsigned)nb * j2;
+            u.e = 0; u.estep = 0;
+        }
         return u;
     }
     NDFB_DEV void next(Cur& u, Cx<R> val) const {
         Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
         if (MODE == 1) { y = cmul(y, ldg(u.t)); u.t += u.tstep; }   // four-step twiddle W_N^{k j2}, k = b + q nb
+        if (MODE == 4) {
+            const Cx<R> w = shift >= 40 ? ldg(&fs[(unsigned)u.e]) : cmul(ldg(&hi[u.e >> shift]), ldg(&fs[u.e & ((1ull << shift) - 1)]));
+            y = cmul(y, cmul(w, ldg(u.t)));
+            u.t += u.tstep; u.e += u.estep;
+        }
         if (valid) *u.p = y;
         u.p += u.step;
     }
@@ -390,10 +408,12 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
     const bool valid = c.valid;
     const int j2 = lb.j2;
     Cx<R> v[S::E];
-    if constexpr (MODE == 0 || MODE == 1) {
+    if constexpr (MODE == 0 || MODE == 1 || MODE == 4) {
         SfftGLoad<R, CG> gl; gl.in = in; gl.is_axis = is_axis; gl.sgn = sgn_in; gl.valid = valid;
         SfftGStore<R, MODE> gs; gs.out = out; gs.os_axis = os_axis; gs.sc = sc; gs.sy = sy; gs.valid = valid;
         gs.fs = reinterpret_cast<const Cx<R>*>(a.fs_lo); gs.j2 = (unsigned)j2;
+        gs.hi = reinterpret_cast<const Cx<R>*>(a.fs_hi); gs.tq = reinterpret_cast<const Cx<R>*>(a.fs_q); gs.shift = a.fs_shift;
+        gs.j20 = (unsigned)(j2 - c.l); gs.lane = c.l; gs.tl = L;
         SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, gl, gs);
         return;
     }
@@ -696,6 +716,7 @@ __global__ void __launch_bounds__(S::TL* L, MINB) sfft_kernel(const __grid_const
     const LaneBase lb = lane_base(a, g, c.valid, a.fs_dim);
     if (plain && !COLS && a.is_axis == 1 && a.os_axis == 1) sfft_body<R, S, L, COLS, 0, true>(a, c, lb, blockIdx.x);
     else if (plain) sfft_body<R, S, L, COLS, 0, false>(a, c, lb, blockIdx.x);
+    else if (COLS && a.fs_twiddle && a.fs_q && !a.os_blk) sfft_body<R, S, L, COLS, 4, false>(a, c, lb, blockIdx.x);
     else if (a.fs_twiddle && a.fs_shift >= 40 && !a.os_blk) sfft_body<R, S, L, COLS, 1, false>(a, c, lb, blockIdx.x);
     else if (kSfftBulkStore<S, COLS> && a.bulk_store) {
         if constexpr (kSfftBulkStore<S, COLS>) sfft_body<R, S, L, COLS, 3, false>(a, c, lb, blockIdx.x);

@@ -721,3 +721,30 @@ def test_mirror_paired_output_pass(hs, op, n, rd, capfd):
         hs.run(op, n, (5, n), 1, rd, seed=n + 1, norm="none")
     finally:
         del os.environ["NDFB_TRACE"]; del os.environ["NDFB_MIRROR_OUT"]
+
+
+def test_four_step_twiddle_factored(hs, capfd):
+    """Column passes of the two- and three-pass splits form W_N^{k j2} as (tile-uniform lookup) x ([k][l] table): single-table
+    lengths (N <= 2^17), the hi/lo product beyond, the nested split, forward and inverse; NDFB_NO_FS_FACTORED keeps the per-point
+    lookups and gives the same result within rounding."""
+    import os
+    os.environ.update({"NDFB_TRACE": "1", "NDFB_FS_CAP": "512"})
+    try:
+        hs.run("ndfft", 64 * 512, (2, 64 * 512), 1, np.float32, seed=1)
+        hs.run("ndifft", 128 * 256, (1, 128 * 256), 1, np.float64, seed=2)
+        os.environ["NDFB_FS_N1"] = "512"
+        hs.run("ndfft", 512 * 512, (1, 512 * 512), 1, np.float32, seed=3)          # 2^18: hi / lo tables
+        del os.environ["NDFB_FS_N1"]
+        err = capfd.readouterr().err
+        assert err.count("four-step twiddle factored") == 3, err
+        os.environ.update({"NDFB_FS_CAP": "256", "NDFB_FS_N1": "64"})
+        hs.run("ndfft", 64 * 64 * 64, (1, 64 * 64 * 64), 1, np.float64, seed=4)    # three passes: both column passes carry a twiddle
+        err = capfd.readouterr().err
+        assert err.count("four-step twiddle factored") == 2, err
+        del os.environ["NDFB_FS_N1"]
+        os.environ["NDFB_NO_FS_FACTORED"] = "1"
+        hs.run("ndfft", 64 * 64, (3, 64 * 64), 1, np.float32, seed=5)
+        assert "four-step twiddle factored" not in capfd.readouterr().err
+    finally:
+        for k in ("NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_NO_FS_FACTORED"):
+            os.environ.pop(k, None)
