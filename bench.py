@@ -423,7 +423,7 @@ class ConfigBench:
         self.add("c5a+", "ndfft axis0 n=1009 (prime: fused Bluestein) 1009x4096 c128", "f64", med, mn, 2 * x.numel() * 16, 4096 * 5.0 * 1009 * math.log2(1009))
         del x, y
 
-    # ---- c5b: 2^24-point rows, batch 64, c64 (four-step: two HBM passes) ----
+    # ---- c5b: 2^24-point rows, batch 64, c64 (multi-pass through a device workspace) ----
     def c5b(self):
         nb, np, t = self.nb, self.np, self.torch
         from oracle import ndrustfft_oracle as orc
@@ -441,9 +441,10 @@ class ConfigBench:
             del xs, ys
         med, mn = self.time_call(lambda: nb.ndfft(x, y, h, 1), iters=max(3, self.iters // 3))
         nbytes = 2 * x.numel() * 8
-        self.add("c5b", "ndfft axis1 64 x 2^24 c64 (four-step)", "f32", med, mn, nbytes, fl, cpu=cpu,
+        self.add("c5b", "ndfft axis1 64 x 2^24 c64 (multi-pass: 64 x 512 x 512)", "f32", med, mn, nbytes, fl, cpu=cpu,
                  frac_of_two_pass_bound=round(2 * nbytes / (med * 1e-3) / 1e9 / self.peak, 4),
-                 note="frac uses the one-pass byte definition; two HBM passes are unavoidable at this length")
+                 note="frac uses the one-pass byte definition; at least two HBM passes are unavoidable at this length, and the library takes "
+                      "three over 256-byte rows (two passes over 32-byte rows measure slower: DESIGN.md 4.4)")
         del x, y
 
 

@@ -562,7 +562,9 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
         int rc = get_fs_kl<R>(p, s.fs.ntot, e->N, e->L, &tq);
         if (rc) return rc;
         a.fs_q = tq;
-        if (std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] four-step twiddle factored: tile-uniform lookup x [k][l] table (%d x %d)\n", e->N, e->L);
+        // room behind the exchange buffer for the tile's own factor W_N^{k j20}, k < N1 (looked up once per tile)
+        launch_smem_floor() = std::max(launch_smem_floor(), e->smem + (size_t)e->N * sizeof(Cx<R>));
+        if (std::getenv("NDFB_TRACE")) fprintf(stderr, "[ndfb] fs twiddle factored: tile-uniform lookup x [k][l] table (%d x %d)\n", e->N, e->L);
     }
     // long contiguous rows: every CTA asks the L2 for the row that will be started when it retires (NDFB_L2_PREFETCH=<waves>, 0 = off)
     // Measured on B200 (tools/ab_l2_prefetch.py, profiles/round2/r2k_ab_l2_prefetch.jsonl): half a wave ahead gains 2-4 % on 32-64 KiB
@@ -1082,8 +1084,8 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             }
         }
     }
-    long long best1 = 0;
-    int best_score = -1;
+    long long best1 = 0, nested1 = 0;
+    int best_score = -1, nested_score = -1;
     for (long long d = 1; d * d <= N; ++d) {
         if (N % d) continue;
         long long cands[2] = {d, N / d};
@@ -1093,14 +1095,13 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             if (n1 > cap1 || n1 < 2 || n2 < 2) continue;
             if (nested && (depth > 0 || strided_lanes || n2 > cap1 * cap2 || (int)dims.size() + 2 > kMaxBatchDims)) continue;
             if (const char* f = std::getenv("NDFB_FS_N1")) { if (depth == 0 && atoll(f) != n1) continue; }
-            else if (nested && n1 != 256) continue;    // three-pass split: 256-point first pass (256-byte rows in f32)
+            else if (nested && n1 != 256 && n1 != 64) continue;    // three-pass split: 64- or 256-point first pass (256-byte rows)
             int score = nested ? 1 : 0;
             if (nested) {
                 const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
                 if (e1 && (size_t)e1->L * cs >= 128) score += 2;
-                // measured on B200 (2^24 f32 x 64): 256 x (256 x 256) 22.8 ms vs 2048 x 8192 15.1 ms, so any two-pass split with
-                // instantiated schedules outranks the three-pass one; it remains the fallback for lengths beyond two factors
-                if (score > best_score) { best_score = score; best1 = n1; }
+                // two-pass splits whose tiles are at least 64 bytes wide outrank the three-pass ones (decided after the loop)
+                if (score > nested_score || (score == nested_score && n1 < nested1)) { nested_score = score; nested1 = n1; }
                 continue;
             }
             const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
@@ -1114,6 +1115,10 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
     }
+    // Two passes whose tile rows are only 32 bytes wide (2^24 = 4096 x 4096 in f32) are bounded by what HBM gives such tiles (~0.5 of
+    // the copy rate per pass): three passes over 256-byte rows win there.  Measured on B200, 64 x 2^24 c64
+    // (profiles/round2/r2v_c5b_variants.txt): 64 x (512 x 512) 10.28 ms, 256^3 10.54 ms, 4096 x 4096 11.33 ms.
+    if (nested1 && (best_score < 6 || !best1) && nested_score >= (best1 ? 3 : 0)) { best1 = nested1; best_score = nested_score; }
     if (!best1) return fail(NDFB_E_UNSUPPORTED, "length %lld is too long for the two-pass decomposition (max about %lld)", N, cap1 * cap2);
     const long long N1 = best1, N2 = N / N1;
     if ((int)dims.size() + 1 > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "four-step transform with more than %d batch dims", kMaxBatchDims - 1);

@@ -140,24 +140,25 @@ struct SfftGLoad {
     }
 };
 // MODE 4: the four-step twiddle W_N^{k j2} of lane j2 = j20 + l (tile base + lane within the tile) factored as
-// W_N^{k j20} (index the same for every lane of the tile: warp-uniform hi / lo lookups) x W_N^{k l} (a plan-owned table [k][l] of
-// N1 x L entries, read coalesced across the lanes, L1-resident).  MODE 1 / 2 look W_N^{k j2} up per point with a per-lane index:
+// W_N^{k j20} (the same for every lane of the tile: N1 values per tile, looked up ONCE by the CTA into shared memory behind the
+// exchange buffer and read back as broadcasts) x W_N^{k l} (a plan-owned table [k][l] of N1 x L entries, read coalesced across the
+// lanes, L1-resident).  MODE 1 / 2 look W_N^{k j2} up per point with a per-lane index:
 // 32 different table lines per warp request (the column passes of the 2^24-point rows of c5b: 4.4-4.6 ms per pass against 2.7 ms
 // for the pass without a twiddle; profiles/round2/r2u_c5b_launches_*.csv).
 template <typename R, int MODE>
 struct SfftGStore {
     static constexpr bool kStrided = true;
     Cx<R>* out; long long os_axis; R sc, sy; bool valid; const Cx<R>* fs; unsigned j2;
-    const Cx<R>* hi; const Cx<R>* tq; int shift; unsigned j20; int lane, tl;   // MODE 4
-    struct Cur { Cx<R>* p; long long step; const Cx<R>* t; unsigned tstep; unsigned long long e, estep; };
+    const Cx<R>* tq; const Cx<R>* wk; int lane, tl;   // MODE 4: [k][l] table, the tile's W_N^{k j20} in shared memory
+    struct Cur { Cx<R>* p; long long step; const Cx<R>* t; unsigned tstep; const Cx<R>* w; };
     NDFB_DEV Cur start(int b, int nb) const {
         Cur u; u.p = out + (long long)b * os_axis; u.step = (long long)nb * os_axis;
         if (MODE == 4) {
             u.t = tq + (unsigned)b * (unsigned)tl + (unsigned)lane; u.tstep = (unsigned)nb * (unsigned)tl;
-            u.e = (unsigned long long)b * j20; u.estep = (unsigned long long)nb * j20;
+            u.w = wk + b;
         } else {
             u.t = fs + (unsigned)b * j2; u.tstep = (unsigned)nb * j2;
-            u.e = 0; u.estep = 0;
+            u.w = nullptr;
         }
         return u;
     }
@@ -165,9 +166,8 @@ struct SfftGStore {
         Cx<R> y = cmake<R>(val.x * sc, val.y * sy);
         if (MODE == 1) { y = cmul(y, ldg(u.t)); u.t += u.tstep; }   // four-step twiddle W_N^{k j2}, k = b + q nb
         if (MODE == 4) {
-            const Cx<R> w = shift >= 40 ? ldg(&fs[(unsigned)u.e]) : cmul(ldg(&hi[u.e >> shift]), ldg(&fs[u.e & ((1ull << shift) - 1)]));
-            y = cmul(y, cmul(w, ldg(u.t)));
-            u.t += u.tstep; u.e += u.estep;
+            y = cmul(y, cmul(*u.w, ldg(u.t)));
+            u.t += u.tstep; u.w += u.tstep / (unsigned)tl;
         }
         if (valid) *u.p = y;
         u.p += u.step;
@@ -412,8 +412,22 @@ NDFB_DEV void sfft_body(const SfftArgs& a, const SfftCtx<R, S, L, COLS>& c, cons
         SfftGLoad<R, CG> gl; gl.in = in; gl.is_axis = is_axis; gl.sgn = sgn_in; gl.valid = valid;
         SfftGStore<R, MODE> gs; gs.out = out; gs.os_axis = os_axis; gs.sc = sc; gs.sy = sy; gs.valid = valid;
         gs.fs = reinterpret_cast<const Cx<R>*>(a.fs_lo); gs.j2 = (unsigned)j2;
-        gs.hi = reinterpret_cast<const Cx<R>*>(a.fs_hi); gs.tq = reinterpret_cast<const Cx<R>*>(a.fs_q); gs.shift = a.fs_shift;
-        gs.j20 = (unsigned)(j2 - c.l); gs.lane = c.l; gs.tl = L;
+        gs.tq = reinterpret_cast<const Cx<R>*>(a.fs_q); gs.lane = c.l; gs.tl = L; gs.wk = nullptr;
+        if constexpr (MODE == 4) {
+            // the tile's own factor W_N^{k j20}, k < N: one hi / lo lookup per k and TILE (not per point), kept behind the exchange
+            // buffer (the host adds N elements to the launch's shared memory); the barriers of the exchanges order it before the
+            // last pass reads it
+            Cx<R>* wk = c.smem + (S::NP > 1 ? (size_t)L * S::NPAD : 0);
+            const Cx<R>* __restrict__ lo = reinterpret_cast<const Cx<R>*>(a.fs_lo);
+            const Cx<R>* __restrict__ hi = reinterpret_cast<const Cx<R>*>(a.fs_hi);
+            const unsigned j20 = (unsigned)(j2 - c.l);     // first lane of the tile: the same value in every thread
+            for (int k = threadIdx.x; k < S::N; k += S::TL * L) {
+                const unsigned long long e = (unsigned long long)k * j20;
+                wk[k] = a.fs_shift >= 40 ? ldg(&lo[(unsigned)e]) : cmul(ldg(&hi[e >> a.fs_shift]), ldg(&lo[e & ((1ull << a.fs_shift) - 1)]));
+            }
+            if (S::NP == 1) __syncthreads();
+            gs.wk = wk;
+        }
         SfftAll<R, S, L, COLS, 0, false, false>::run(c, v, tw, gl, gs);
         return;
     }

@@ -736,15 +736,15 @@ def test_four_step_twiddle_factored(hs, capfd):
         hs.run("ndfft", 512 * 512, (1, 512 * 512), 1, np.float32, seed=3)          # 2^18: hi / lo tables
         del os.environ["NDFB_FS_N1"]
         err = capfd.readouterr().err
-        assert err.count("four-step twiddle factored") == 3, err
+        assert err.count("fs twiddle factored") == 3, err
         os.environ.update({"NDFB_FS_CAP": "256", "NDFB_FS_N1": "64"})
         hs.run("ndfft", 64 * 64 * 64, (1, 64 * 64 * 64), 1, np.float64, seed=4)    # three passes: both column passes carry a twiddle
         err = capfd.readouterr().err
-        assert err.count("four-step twiddle factored") == 2, err
+        assert err.count("fs twiddle factored") == 2, err
         del os.environ["NDFB_FS_N1"]
         os.environ["NDFB_NO_FS_FACTORED"] = "1"
         hs.run("ndfft", 64 * 64, (3, 64 * 64), 1, np.float32, seed=5)
-        assert "four-step twiddle factored" not in capfd.readouterr().err
+        assert "fs twiddle factored" not in capfd.readouterr().err
     finally:
         for k in ("NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_NO_FS_FACTORED"):
             os.environ.pop(k, None)

@@ -1,15 +1,15 @@
 #!/bin/bash
 # factored four-step twiddle in the column kernels (MODE 4): parity, c5b splits with / without it, per-launch times
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "four_step or config5b or three_pass or fused_two_pass or config2 or in_place" > gpurun_out/r2v_pytest.log 2>&1; tail -3 gpurun_out/r2v_pytest.log
-timeout 900 python tools/exp_c5b2.py > gpurun_out/r2v_c5b_variants.txt 2> gpurun_out/r2v.err; grep -E "^\{" gpurun_out/r2v_c5b_variants.txt
+timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "four_step or config5b or three_pass or fused_two_pass or config2 or in_place" > gpurun_out/r2w_pytest.log 2>&1; tail -3 gpurun_out/r2w_pytest.log
+timeout 900 python tools/exp_c5b2.py > gpurun_out/r2w_c5b_variants.txt 2> gpurun_out/r2w.err; grep -E "^\{" gpurun_out/r2w_c5b_variants.txt
 for v in 4096 256 64; do
   export NDFB_FS_N1=$v
-  SHAPE=64x16777216 AXIS=1 F64=0 ITERS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2v_c5b_launches_$v.csv python tools/run_one.py > /dev/null 2>&1
+  SHAPE=64x16777216 AXIS=1 F64=0 ITERS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2w_c5b_launches_$v.csv python tools/run_one.py > /dev/null 2>&1
   echo "== FS_N1=$v"
   python - "$v" <<'PY'
 import csv, sys
-rows = list(csv.reader(open('gpurun_out/r2v_c5b_launches_%s.csv' % sys.argv[1])))
+rows = list(csv.reader(open('gpurun_out/r2w_c5b_launches_%s.csv' % sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 for r in rows[hdr + 1:]:
     if 'sfft' in r[4]: print('   ', r[4][:100], r[-1], r[-2])
