@@ -441,7 +441,7 @@ class ConfigBench:
             del xs, ys
         med, mn = self.time_call(lambda: nb.ndfft(x, y, h, 1), iters=max(3, self.iters // 3))
         nbytes = 2 * x.numel() * 8
-        self.add("c5b", "ndfft axis1 64 x 2^24 c64 (multi-pass: 64 x 512 x 512)", "f32", med, mn, nbytes, fl, cpu=cpu,
+        self.add("c5b", "ndfft axis1 64 x 2^24 c64 (multi-pass: 256 x 256 x 256)", "f32", med, mn, nbytes, fl, cpu=cpu,
                  frac_of_two_pass_bound=round(2 * nbytes / (med * 1e-3) / 1e9 / self.peak, 4),
                  note="frac uses the one-pass byte definition; at least two HBM passes are unavoidable at this length, and the library takes "
                       "three over 256-byte rows (two passes over 32-byte rows measure slower: DESIGN.md 4.4)")

@@ -1042,6 +1042,10 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     long long cap1 = (long long)((cap - 256) / (4 * cs));  // pass 1 wants >= 4 lanes per tile (32-byte rows)
     long long cap2 = (long long)((cap - 256) / cs);
     if (const char* f = std::getenv("NDFB_FS_CAP")) cap1 = cap2 = atoll(f);   // test hook: pretend the chip is tiny
+    // Soft cap of the second factor.  Measured on B200 (profiles/round2/r2x_fs_medium.txt, 4.3 GB arrays): with both factors >= 1024 the
+    // passes run one 139 KB tile per SM at ~0.5 of the copy rate, three passes over small tiles run at ~0.9 each:
+    // 2^20 c64 5.45 -> 4.02 ms, 2^22 c64 5.10 -> 4.09 ms, 2^20 c128 5.37 -> 4.13 ms, 2^22 c128 5.50 -> 4.44 ms.
+    const long long cap2s = std::getenv("NDFB_FS_CAP") || std::getenv("NDFB_FS_TWO_PASS") ? cap2 : std::min<long long>(cap2, 512);
     if (!is_smooth(N)) return fail(NDFB_E_UNSUPPORTED, "length %lld has a prime factor > 13 and is too long for the single-pass Bluestein kernel", N);
     // N1 * N2 = N with both factors on chip; prefer factors that have an instantiated Stockham schedule (and, for the
     // column pass, a tile at least one 32-byte sector wide), then the most square split
@@ -1091,9 +1095,13 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
         long long cands[2] = {d, N / d};
         for (long long n1 : cands) {
             long long n2 = N / n1;
-            const bool nested = n2 > cap2;
+            // second factors beyond 512 points run one CTA per SM (128 KB tiles): where a third pass is possible it is preferred
+            bool nested = n2 > cap2s;
             if (n1 > cap1 || n1 < 2 || n2 < 2) continue;
-            if (nested && (depth > 0 || strided_lanes || n2 > cap1 * cap2 || (int)dims.size() + 2 > kMaxBatchDims)) continue;
+            if (nested && (depth > 0 || strided_lanes || n2 > cap1 * cap2 || (int)dims.size() + 2 > kMaxBatchDims)) {
+                if (n2 > cap2) continue;
+                nested = false;         // no third pass here: the big second-factor tile it is
+            }
             if (const char* f = std::getenv("NDFB_FS_N1")) { if (depth == 0 && atoll(f) != n1) continue; }
             else if (nested && n1 != 256 && n1 != 64) continue;    // three-pass split: 64- or 256-point first pass (256-byte rows)
             int score = nested ? 1 : 0;
@@ -1101,7 +1109,8 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
                 const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
                 if (e1 && (size_t)e1->L * cs >= 128) score += 2;
                 // two-pass splits whose tiles are at least 64 bytes wide outrank the three-pass ones (decided after the loop)
-                if (score > nested_score || (score == nested_score && n1 < nested1)) { nested_score = score; nested1 = n1; }
+                // ties: the 256-point first pass (64 x 2^24 c64: 256^3 8.55 ms, 128 x .. 8.60, 64 x (512 x 512) 8.89, 512 x .. 8.99)
+                if (score > nested_score || (score == nested_score && n1 > nested1)) { nested_score = score; nested1 = n1; }
                 continue;
             }
             const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
@@ -1112,13 +1121,15 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             if (e1 && (size_t)e1->L * cs >= 64) score += 1;
             if (e2 && (size_t)e2->L * cs >= 32) score += 2;
             if (e2 && (size_t)e2->L * cs >= 64) score += 1;
+            if (std::max(n1, n2) > 512 && score > 0) score -= 1;      // a 128 KB tile in one of the passes
             if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
     }
     // Two passes whose tile rows are only 32 bytes wide (2^24 = 4096 x 4096 in f32) are bounded by what HBM gives such tiles (~0.5 of
     // the copy rate per pass): three passes over 256-byte rows win there.  Measured on B200, 64 x 2^24 c64
     // (profiles/round2/r2v_c5b_variants.txt): 64 x (512 x 512) 10.28 ms, 256^3 10.54 ms, 4096 x 4096 11.33 ms.
-    if (nested1 && (best_score < 6 || !best1) && nested_score >= (best1 ? 3 : 0)) { best1 = nested1; best_score = nested_score; }
+    bool pick_nested = false;
+    if (nested1 && (best_score < 6 || !best1) && nested_score >= (best1 ? 3 : 0)) { best1 = nested1; best_score = nested_score; pick_nested = true; }
     if (!best1) return fail(NDFB_E_UNSUPPORTED, "length %lld is too long for the two-pass decomposition (max about %lld)", N, cap1 * cap2);
     const long long N1 = best1, N2 = N / N1;
     if ((int)dims.size() + 1 > kMaxBatchDims) return fail(NDFB_E_UNSUPPORTED, "four-step transform with more than %d batch dims", kMaxBatchDims - 1);
@@ -1127,7 +1138,7 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     void* ws = nullptr;
     int rc = g_pool.get(depth == 0 ? 2 : 5, p->device, (size_t)nb * (size_t)N * cs, &ws);
     if (rc) return rc;
-    const bool nested2 = N2 > cap2;
+    const bool nested2 = pick_nested;
     Core* c1 = get_core(p, TK_C2C, (int)N1);
     Core* c2 = nested2 ? nullptr : get_core(p, TK_C2C, (int)N2);
     if ((rc = ensure_device<R>(p, c1))) return rc;
@@ -1510,7 +1521,7 @@ static int exec_device(ndfb_plan* p, const OpInfo& o, double extra_scale, const 
         // the multi-pass paths index fewer batch dims in their kernels (the passes add dims of their own): peel the rest
         const bool four_step = o.tk == TK_C2C && is_smooth((long long)p->n) && !std::getenv("NDFB_FORCE_STAGED");
         int lim = kMaxBatchDims;
-        if (four_step) lim = ((long long)p->n > (1LL << 24) || std::getenv("NDFB_FS_CAP")) ? kMaxBatchDims - 2 : kMaxBatchDims - 1;
+        if (four_step) lim = ((long long)p->n > (1LL << 18) || std::getenv("NDFB_FS_CAP")) ? kMaxBatchDims - 2 : kMaxBatchDims - 1;   // three passes add two dims
         return peel_batch_dims(dims, lim, ie, oe, in, out, nullptr, 0, [&](const void* pin, void* pout, const std::vector<BDim>& d2, void* const*) -> int {
             if (four_step) return exec_four_step<R>(p, (long long)p->n, o.conj_in != 0, scale, pin, pout, d2, is_axis, os_axis, stream);
             return exec_big<R>(p, o, scale, pin, pout, d2, is_axis, os_axis, stream);

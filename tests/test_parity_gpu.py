@@ -550,8 +550,8 @@ def test_workspace_reuse_across_streams(dev):
 
 
 def test_three_pass_split_matches_two_pass(dev, capfd):
-    # 2^24-point rows: the default is three passes over 256-byte rows, 64 x (512 x 512); forced 4096 x 4096 (two passes over 32-byte
-    # rows) and 256 x (256 x 256): the nested level's last pass tiles the lanes along the output-contiguous dim (transposing pass).
+    # 2^24-point rows: the default is three passes over 256-byte rows, 256 x (256 x 256); forced 4096 x 4096 (two passes over 32-byte
+    # rows) and 128 x (...): the nested level's last pass tiles the lanes along the output-contiguous dim (transposing pass).
     # Same transform, different factorisations: equal within f32 rounding.
     import os
     be = dev.be
@@ -562,17 +562,18 @@ def test_three_pass_split_matches_two_pass(dev, capfd):
     os.environ["NDFB_TRACE"] = "1"
     try:
         be.ndfft(x, yd, h, 1)
-        assert "= 64 x 262144" in capfd.readouterr().err
-        os.environ["NDFB_FS_N1"] = "4096"
+        assert "= 256 x 65536" in capfd.readouterr().err
+        os.environ["NDFB_FS_N1"] = "4096"; os.environ["NDFB_FS_TWO_PASS"] = "1"
         be.ndfft(x, y2, h, 1)
-        assert "= 4096 x 4096" in capfd.readouterr().err
-        os.environ["NDFB_FS_N1"] = "256"
+        assert "= 4096 x 4096 (contiguous lanes)" in capfd.readouterr().err
+        del os.environ["NDFB_FS_TWO_PASS"]
+        os.environ["NDFB_FS_N1"] = "128"
         be.ndfft(x, y3, h, 1)
         assert _rel(y3, y2) < 2e-6 and _rel(yd, y2) < 2e-6
         be.ndifft(y3, y3, h, 1)          # in place through the three-pass path
         assert _rel(y3, x) < 2e-6
     finally:
-        os.environ.pop("NDFB_FS_N1", None); os.environ.pop("NDFB_TRACE", None)
+        os.environ.pop("NDFB_FS_N1", None); os.environ.pop("NDFB_TRACE", None); os.environ.pop("NDFB_FS_TWO_PASS", None)
     _lane_subset_check(be, "ndfft", n, x, yd, 1, np.float32, nsample=1)
 
 

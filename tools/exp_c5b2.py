@@ -22,7 +22,7 @@ want = np.fft.fft(x[:2].cpu().numpy().astype(np.complex128), axis=1)
 rel = float(np.linalg.norm(sub - want) / np.linalg.norm(want))
 print(json.dumps({"variant": os.environ.get("VARIANT"), "ms": ts[len(ts)//2], "frac_one_pass_bytes": 2 * x.numel() * 8 / (ts[len(ts)//2] * 1e-3) / 1e9 / 6547.8, "rel_l2": rel}))
 ''' % ROOT
-for name, env in (("two-pass 4096x4096", {"NDFB_FS_N1": "4096"}), ("two-pass 4096x4096, per-point twiddle lookups", {"NDFB_FS_N1": "4096", "NDFB_NO_FS_FACTORED": "1"}),
+for name, env in (("two-pass 4096x4096", {"NDFB_FS_N1": "4096", "NDFB_FS_TWO_PASS": "1"}), ("two-pass 4096x4096, per-point twiddle lookups", {"NDFB_FS_N1": "4096", "NDFB_FS_TWO_PASS": "1", "NDFB_NO_FS_FACTORED": "1"}),
                   ("default split", {}),
                   ("three-pass 256x256x256 transposing rows", {"NDFB_FS_N1": "256"}),
                   ("three-pass 256x256x256, per-point twiddle lookups", {"NDFB_FS_N1": "256", "NDFB_NO_FS_FACTORED": "1"}),
