@@ -1109,8 +1109,10 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
                 const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
                 if (e1 && (size_t)e1->L * cs >= 128) score += 2;
                 // two-pass splits whose tiles are at least 64 bytes wide outrank the three-pass ones (decided after the loop)
-                // ties: the 256-point first pass (64 x 2^24 c64: 256^3 8.55 ms, 128 x .. 8.60, 64 x (512 x 512) 8.89, 512 x .. 8.99)
-                if (score > nested_score || (score == nested_score && n1 > nested1)) { nested_score = score; nested1 = n1; }
+                // ties: f32 the 256-point first pass (64 x 2^24 c64: 256^3 8.55 ms, 128 x .. 8.60, 64 x (512 x 512) 8.89, 512 x .. 8.99),
+                // f64 the 64-point one (2^20 c128: 4.13 vs 4.33 ms, 2^21: 4.21 vs 4.36 ms; profiles/round2/r2y_fs_medium.txt)
+                const bool prefer = sizeof(R) == 4 ? n1 > nested1 : (nested1 == 0 || n1 < nested1);
+                if (score > nested_score || (score == nested_score && prefer)) { nested_score = score; nested1 = n1; }
                 continue;
             }
             const SfftEntry* e1 = find_sfft(sizeof(R) == 8, (int)n1, true, 1 << 20);
