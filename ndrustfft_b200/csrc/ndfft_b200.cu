@@ -1182,7 +1182,15 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
     s1.conj_in = conj_in; s1.fs_twiddle = 1; s1.fs = fs;
     if ((rc = launch_c2c<R>(p, s1, stream))) return rc;
     s2.conj_out = inverse; s2.scale = scale;
-    if (!nested2 && !strided && (depth > 0 || std::getenv("NDFB_FS_TRANSPOSE")) && !std::getenv("NDFB_NO_FS_TRANSPOSE")) {
+    if (!nested2 && !strided && depth == 0 && !std::getenv("NDFB_NO_FS_TRANSPOSE") && !std::getenv("NDFB_NO_TRANS_STORE")) {
+        // Last pass of a TWO-pass split: its lanes k1 are rows of the workspace (N2 elements apart) and adjacent elements of the
+        // output — the transposing rows kernel's case as it stands (launch_c2c falls back to the column tile when there is no
+        // multi-lane row schedule for N2 or the output rows are not contiguous).  Measured on B200, 8192 rows of 2^16 points c64
+        // (profiles/round2/r3a_launches_*.csv): the column tile reads 32 lanes x 8 bytes per warp request and takes 2.67 ms where the
+        // first pass takes 1.45 ms.
+        s2.trans = true;
+    }
+    if (!nested2 && !strided && depth > 0 && !std::getenv("NDFB_NO_FS_TRANSPOSE")) {
         // Transposing last pass of the three-pass split: tile the lanes along the dim that is contiguous in the OUTPUT (the
         // outer level's k1, output stride 1) instead of the one contiguous in the workspace, and cap the tile at 8 lanes
         // so that a warp still reads 32/L consecutive points (>= one 32-byte sector) of each lane's row.  Measured on

@@ -690,7 +690,7 @@ def test_pipelined_column_kernel_four_step(hs, capfd):
     """Both passes of a two-pass split on the pipelined kernel: pass 1 reads lane-adjacent rows and applies the four-step twiddle
     in its store, pass 2 reads contiguous workspace rows (row staging layout) and stores lane-interleaved."""
     import os
-    os.environ.update({"NDFB_PIPE": "2", "NDFB_TRACE": "1", "NDFB_FS_CAP": "512", "NDFB_FS_N1": "64"})
+    os.environ.update({"NDFB_PIPE": "2", "NDFB_TRACE": "1", "NDFB_FS_CAP": "512", "NDFB_FS_N1": "64", "NDFB_NO_FS_TRANSPOSE": "1"})
     try:
         hs.run("ndfft", 64 * 512, (2, 64 * 512), 1, np.float32, seed=7)
         hs.run("ndifft", 64 * 512, (1, 64 * 512), 1, np.float64, seed=8)
@@ -702,7 +702,7 @@ def test_pipelined_column_kernel_four_step(hs, capfd):
         err = capfd.readouterr().err
         assert err.count("in=lane-adjacent") == 1 and err.count("in=rows") == 1, err
     finally:
-        for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1"):
+        for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_NO_FS_TRANSPOSE"):
             os.environ.pop(k, None)
 
 

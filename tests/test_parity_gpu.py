@@ -809,13 +809,13 @@ def test_pipelined_column_kernel_gpu(dev, capfd):
     x = _rand((6, n), np.float32, True, 77)
     h = be.FftHandler(n, np.float32)
     y0 = torch.empty_like(x); y1 = torch.empty_like(x)
-    os.environ.update({"NDFB_PIPE": "0", "NDFB_FS_N1": "4096", "NDFB_FS_TWO_PASS": "1"})     # the two-pass split: 4 x 4096 tiles in both passes
+    os.environ.update({"NDFB_PIPE": "0", "NDFB_FS_N1": "4096", "NDFB_FS_TWO_PASS": "1", "NDFB_NO_FS_TRANSPOSE": "1"})     # the two-pass split: 4 x 4096 tiles in both passes
     try:
         be.ndfft(x, y0, h, 1)
         os.environ["NDFB_PIPE"] = "2"; os.environ["NDFB_TRACE"] = "1"
         be.ndfft(x, y1, h, 1)
     finally:
-        for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_N1", "NDFB_FS_TWO_PASS"):
+        for k in ("NDFB_PIPE", "NDFB_TRACE", "NDFB_FS_N1", "NDFB_FS_TWO_PASS", "NDFB_NO_FS_TRANSPOSE"):
             os.environ.pop(k, None)
     err = capfd.readouterr().err
     assert err.count("in=lane-adjacent") == 1 and err.count("in=rows") == 1, err
