@@ -1123,7 +1123,6 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             if (e1 && (size_t)e1->L * cs >= 64) score += 1;
             if (e2 && (size_t)e2->L * cs >= 32) score += 2;
             if (e2 && (size_t)e2->L * cs >= 64) score += 1;
-            if (std::max(n1, n2) > 512 && score > 0) score -= 1;      // a 128 KB tile in one of the passes
             if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
     }
