@@ -1123,6 +1123,9 @@ static int exec_four_step(ndfb_plan* p, long long N, bool inverse, double scale,
             if (e1 && (size_t)e1->L * cs >= 64) score += 1;
             if (e2 && (size_t)e2->L * cs >= 32) score += 2;
             if (e2 && (size_t)e2->L * cs >= 64) score += 1;
+            // f64: a first factor beyond 512 points (147 KB tiles) loses to three passes (2^19: 4.10 vs 3.90 ms, 2^20: 4.48 vs 4.16 ms);
+            // f32 it wins while its tile rows stay >= 64 bytes (2^19: 3.58 vs 4.38 ms, 2^20: 3.92 vs 4.31 ms; profiles/round2/r3b, r3c_fs_medium.txt)
+            if (sizeof(R) == 8 && std::max(n1, n2) > 512 && score > 0) score -= 1;
             if (score > best_score || (score == best_score && llabs_(n1 - n2) < llabs_(best1 - N / best1))) { best_score = score; best1 = n1; }
         }
     }
