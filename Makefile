@@ -16,7 +16,7 @@ OBJDIR    := build
 NVOBJS    := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/cuda/%.o,$(SRCS))
 EMUOBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/emu/%.o,$(SRCS))
 
-all: $(LIB) $(EMULIB)
+all: $(LIB) $(EMULIB) probes
 
 # kernel headers embedded as strings for run-time compilation of further schedules (csrc/jit.h)
 $(CSRC)/jit_sources.inc: $(CSRC)/common.h $(CSRC)/butterflies.cuh $(CSRC)/sfft_kernel.cuh tools/embed_src.py
@@ -51,7 +51,13 @@ $(LIB): $(NVOBJS)
 $(EMULIB): $(EMUOBJS)
 	$(CXX) -shared -o $@ $(EMUOBJS)
 
-clean:
-	rm -rf $(LIB) $(EMULIB) $(OBJDIR)
+# stand-alone measurement probes (tools/probes/*.cu -> binaries next to their sources)
+PROBES    := $(patsubst %.cu,%,$(wildcard tools/probes/*.cu))
+probes: $(PROBES)
+tools/probes/%: tools/probes/%.cu
+	$(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -o $@ $<
 
-.PHONY: all lib emu clean
+clean:
+	rm -rf $(LIB) $(EMULIB) $(OBJDIR) $(PROBES)
+
+.PHONY: all lib emu probes clean
