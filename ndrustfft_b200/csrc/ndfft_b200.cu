@@ -905,9 +905,9 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             // unless NDFB_MIRROR_OUT=1 asks for it.
             const bool want_mirror = rk == RK_DCT4 || (rk == RK_DCT3 && (sizeof(R) == 4 || std::getenv("NDFB_MIRROR_OUT")));
             if (!cols && s.os_axis == 1 && want_mirror && !std::getenv("NDFB_NO_MIRROR_OUT")) {
-                bool al = ((uintptr_t)s.out % (2 * sizeof(R))) == 0;
-                for (auto& d : s.dims) if (d.os % 2) al = false;
-                a.vec_out = al ? 1 : 0;
+                bool al = ((uintptr_t)s.out % (2 * sizeof(R))) == 0, al4 = ((uintptr_t)s.out % (4 * sizeof(R))) == 0;
+                for (auto& d : s.dims) { if (d.os % 2) al = false; if (d.os % 4) al4 = false; }
+                a.vec_out = al ? (al4 ? 2 : 1) : 0;
                 if (a.vec_out && trace) fprintf(stderr, "[ndfb] real kind=%d rows: mirror-paired output pass where the schedule allows it (aligned contiguous rows)\n", rk);
             }
             SfftEntry proxy;

@@ -943,7 +943,8 @@ struct RsfftArgs {
     long long done_group;
     const void* tabA; // exp(-2 pi i k / (2N)), k <= N   (DCT-IV: exp(-i pi j / n))
     const void* tabB; // DCT-II/III: exp(-i pi k / (2n));  DCT-IV: exp(-i pi (4j+1) / (4n))
-    int vec_out;      // contiguous output rows start on 2-real boundaries: DCT-III / DCT-IV may store pairs of reals (kMirrorOut)
+    int vec_out;      // contiguous output rows start on 2-real (1) / 4-real (2) boundaries: DCT-III / DCT-IV may store pairs / quads of
+                      // reals straight from registers (kMirrorOut)
 };
 
 // UNIT: contiguous rows on both sides (axis strides 1): address arithmetic folds to constants
@@ -1235,6 +1236,23 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
         }
         if (!valid) return;
         auto put2 = [&](int t, R x0, R x1) { *reinterpret_cast<Cx<R>*>(out_r + t) = cmake<R>(x0, x1); };   // t even: aligned pair
+        // four adjacent reals as ONE store when the rows are aligned for it (a.vec_out == 2): a whole 32-byte sector per thread in
+        // f64 (st.global.v4.f64 = STG.E.ENL2.256 on sm_100a) instead of two half-sector stores from the same thread
+        const bool wide = a.vec_out >= 2;
+        auto put4 = [&](int t, R x0, R x1, R x2, R x3) {
+#ifndef NDFB_EMU
+            if (wide) {
+                if constexpr (sizeof(R) == 8) {
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out_r + t), "d"((double)x0), "d"((double)x1), "d"((double)x2), "d"((double)x3) : "memory");
+                } else {
+                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_r + t), "f"((float)x0), "f"((float)x1), "f"((float)x2), "f"((float)x3) : "memory");
+                }
+                return;
+            }
+#endif
+            put2(t, x0, x1);
+            put2(t + 2, x2, x3);
+        };
 #pragma unroll
         for (int m = 0; m < HG; ++m) {
             const int b0 = c.i + S::TL * m;
@@ -1249,8 +1267,7 @@ NDFB_DEV void rsfft_body(const RsfftArgs& a) {
                     const bool klo = q < r / 2;
                     const Cx<R> ylo = klo ? yk : ym, yhi = klo ? ym : yk;
                     const int t = 4 * (klo ? k : N - 1 - k);
-                    put2(t, h * ylo.x, -h * yhi.y);
-                    put2(t + 2, -h * ylo.y, h * yhi.x);
+                    put4(t, h * ylo.x, -h * yhi.y, -h * ylo.y, h * yhi.x);
                 } else {
                     const Cx<R> Ck = cmul(yk, ldg(&tabB[k])), Cm = cmul(ym, ldg(&tabB[N - 1 - k]));
                     put2(2 * k, sc * Ck.x, -sc * Cm.y);                  // out[2k], out[2k+1] = out[n-1-2k']

@@ -39,12 +39,14 @@ nbytes = 2 * x.numel() * x.element_size()
 print(json.dumps({"case": os.environ["CASE"], "variant": os.environ["VARIANT"], "ms": round(ms, 4), "ms_min": round(ts[0], 4),
                   "frac": round(nbytes / (ms * 1e-3) / 1e9 / 6547.8, 4), "rel_l2": orc.rel_l2(ys, want)}))
 ''' % ROOT
+V2 = [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {"NDFB_MIRROR_OUT": "1"})]
 CASES = [  # case, op, shape, axis, f64, [(variant, env)]
-    ("c4 nddct3 rows 4096^2 f64", "nddct3", "4096x4096", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
-    ("c4 nddct4 rows 4096^2 f64", "nddct4", "4096x4096", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
-    ("nddct3 rows 8192x4096 f32", "nddct3", "8192x4096", 1, 0, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
-    ("nddct4 rows 16384x2048 f64", "nddct4", "16384x2048", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
-    ("nddct3 rows 32768x1024 f64", "nddct3", "32768x1024", 1, 1, [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]),
+    ("c4 nddct3 rows 4096^2 f64", "nddct3", "4096x4096", 1, 1, V2),
+    ("c4 nddct4 rows 4096^2 f64", "nddct4", "4096x4096", 1, 1, V2),
+    ("nddct3 rows 8192x4096 f32", "nddct3", "8192x4096", 1, 0, V2),
+    ("nddct4 rows 16384x2048 f64", "nddct4", "16384x2048", 1, 1, V2),
+    ("nddct3 rows 16384x2048 f64", "nddct3", "16384x2048", 1, 1, V2),
+    ("nddct3 rows 32768x1024 f64", "nddct3", "32768x1024", 1, 1, V2),
 ]
 only = sys.argv[1:]
 for case, op, shape, axis, f64, variants in CASES:
