@@ -900,10 +900,10 @@ static int launch_real(ndfb_plan* p, const LaunchSpec& s, stream_t stream) {
             a.tabA = s.core->d.tabA; a.tabB = s.core->d.tabB;
             // contiguous DCT-III / DCT-IV output rows that start on 2-real boundaries: mirror-paired last pass, pairs of reals stored
             // straight from registers (sfft_kernel.cuh: kMirrorOut); NDFB_NO_MIRROR_OUT keeps the staged copy-out (A/B runs)
-            // Measured on B200 (profiles/round2/r2s_ab_mirror_out.jsonl): DCT-IV +10-11 % (4096^2 f64 rows 0.084 -> 0.076 ms), DCT-III f32 +7 %,
-            // DCT-III f64 -3 % (its zip prologue already fills the shared-memory pipe): f64 DCT-III keeps the staged copy-out
-            // unless NDFB_MIRROR_OUT=1 asks for it.
-            const bool want_mirror = rk == RK_DCT4 || (rk == RK_DCT3 && (sizeof(R) == 4 || std::getenv("NDFB_MIRROR_OUT")));
+            // Measured on B200: DCT-IV +10-11 % (4096^2 f64 rows 0.084 -> 0.076 ms), DCT-III f32 +13 %, f64 +6 % once its four reals per
+            // sector go out as ONE 256-bit store (two 16-byte stores per thread, i.e. half sectors per request, lost 3 %:
+            // profiles/round2/r2s_ab_mirror_out.jsonl, r3g_ab_mirror_out_wide.jsonl).  NDFB_NO_MIRROR_OUT keeps the staged copy-out.
+            const bool want_mirror = rk == RK_DCT4 || rk == RK_DCT3;
             if (!cols && s.os_axis == 1 && want_mirror && !std::getenv("NDFB_NO_MIRROR_OUT")) {
                 bool al = ((uintptr_t)s.out % (2 * sizeof(R))) == 0, al4 = ((uintptr_t)s.out % (4 * sizeof(R))) == 0;
                 for (auto& d : s.dims) { if (d.os % 2) al = false; if (d.os % 4) al4 = false; }

@@ -714,7 +714,7 @@ def test_mirror_paired_output_pass(hs, op, n, rd, capfd):
     default and no normalisation.  (Rows that start on an odd element keep the staged copy-out: GPU test, device views.)"""
     import os
     os.environ["NDFB_TRACE"] = "1"
-    os.environ["NDFB_MIRROR_OUT"] = "1"      # f64 DCT-III takes it only on request (measured slower there)
+    os.environ["NDFB_MIRROR_OUT"] = "1"      # (no longer needed: every DCT-III / DCT-IV row call takes it)
     try:
         hs.run(op, n, (3, n), 1, rd, seed=n)
         assert "mirror-paired output" in capfd.readouterr().err

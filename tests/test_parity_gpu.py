@@ -839,7 +839,7 @@ def test_mirror_paired_output_pass_gpu(dev, op, n, rd, capfd):
     h = be.DctHandler(n, rd)
     xd = torch.from_numpy(x).cuda()
     os.environ["NDFB_TRACE"] = "1"
-    os.environ["NDFB_MIRROR_OUT"] = "1"      # f64 DCT-III takes it only on request (measured slower there)
+    os.environ["NDFB_MIRROR_OUT"] = "1"      # (no longer needed: every DCT-III / DCT-IV row call takes it)
     try:
         y = torch.empty_like(xd)
         getattr(be, op)(xd, y, h, 1)
