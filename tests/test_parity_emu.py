@@ -748,3 +748,23 @@ def test_four_step_twiddle_factored(hs, capfd):
     finally:
         for k in ("NDFB_TRACE", "NDFB_FS_CAP", "NDFB_FS_N1", "NDFB_NO_FS_FACTORED"):
             os.environ.pop(k, None)
+
+
+def test_default_split_rules_at_real_sizes(hs, capfd):
+    """The multi-pass split the host picks WITHOUT the test caps: f32 2^19 = 1024 x 512 in two passes with the
+    transposing rows kernel as last pass; f64 2^19 takes three passes (64-point first factor) rather than a 1024-point one."""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run("ndfft", 1 << 19, (1, 1 << 19), 1, np.float32, seed=1)
+        err = capfd.readouterr().err
+        assert "four-step N=524288 = 1024 x 512 (contiguous lanes)" in err and "N=512 rows->lanes (transposing)" in err, err
+        hs.run("ndfft", 1 << 19, (1, 1 << 19), 1, np.float64, seed=2)
+        err = capfd.readouterr().err
+        assert "four-step N=524288 = 64 x 8192 (contiguous lanes, second factor split again)" in err, err
+        assert err.count("fs twiddle factored") == 2 and "rows->lanes (transposing)" in err, err
+        hs.run("ndifft", 1 << 21, (1, 1 << 21), 1, np.float32, seed=3)      # f32 from 2^21: 256 x (a x b)
+        err = capfd.readouterr().err
+        assert "four-step N=2097152 = 256 x 8192 (contiguous lanes, second factor split again)" in err, err
+    finally:
+        del os.environ["NDFB_TRACE"]
