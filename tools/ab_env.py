@@ -39,14 +39,16 @@ nbytes = 2 * x.numel() * x.element_size()
 print(json.dumps({"case": os.environ["CASE"], "variant": os.environ["VARIANT"], "ms": round(ms, 4), "ms_min": round(ts[0], 4),
                   "frac": round(nbytes / (ms * 1e-3) / 1e9 / 6547.8, 4), "rel_l2": orc.rel_l2(ys, want)}))
 ''' % ROOT
-V2 = [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {"NDFB_MIRROR_OUT": "1"})]
+V2 = [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]
+D1R = [("13.9.7.5 on 512 threads, 2 CTAs/SM", {"NDFB_RSFFT_PICK": "4095:1"}), ("15.13.7.3 on 320 threads, 2 CTAs/SM", {"NDFB_RSFFT_PICK": "4095:2"}),
+       ("15.13.7.3 on 320 threads, 3 CTAs/SM", {"NDFB_RSFFT_PICK": "4095:3"})]
+D1C = [("13.9.7.5, two-column tile of 1024 threads", {"NDFB_RSFFT_PICK": "4095:0"}), ("15.13.7.3, two-column tile of 640 threads", {"NDFB_RSFFT_PICK": "4095:1"})]
 CASES = [  # case, op, shape, axis, f64, [(variant, env)]
+    ("c4 nddct1 rows 4096^2 f64", "nddct1", "4096x4096", 1, 1, D1R),
+    ("c4 nddct1 columns 4096^2 f64", "nddct1", "4096x4096", 0, 1, D1C),
+    ("nddct1 rows 8192x4096 f32", "nddct1", "8192x4096", 1, 0, D1R),
     ("c4 nddct3 rows 4096^2 f64", "nddct3", "4096x4096", 1, 1, V2),
     ("c4 nddct4 rows 4096^2 f64", "nddct4", "4096x4096", 1, 1, V2),
-    ("nddct3 rows 8192x4096 f32", "nddct3", "8192x4096", 1, 0, V2),
-    ("nddct4 rows 16384x2048 f64", "nddct4", "16384x2048", 1, 1, V2),
-    ("nddct3 rows 16384x2048 f64", "nddct3", "16384x2048", 1, 1, V2),
-    ("nddct3 rows 32768x1024 f64", "nddct3", "32768x1024", 1, 1, V2),
 ]
 only = sys.argv[1:]
 for case, op, shape, axis, f64, variants in CASES:

@@ -218,6 +218,22 @@ def real_entries(f64):
     return dedup(out)
 
 
+# alternative schedules of a core length, instantiated next to the MIXED one for the real kinds only (the host's entry rules or
+# NDFB_RSFFT_PICK choose): 4095 = 15.13.7.3 on 320 threads wastes fewer thread slots per pass (85-98 % busy against 57-89 % for
+# 13.9.7.5 on 512) and three CTAs fit an SM
+ALT_REAL = {4095: (320, [15, 13, 7, 3])}
+
+
+def alt_real_entries(f64):
+    out = []
+    cs = 16 if f64 else 8
+    for N, (TL, rad) in ALT_REAL.items():
+        for minb in (2, 3):
+            out.append(make(f64, N, TL, rad, 1, 0, 0, minb=minb, always_smem=True))
+        out.append(make(f64, N, TL, rad, 2, 1, 0, minb=1, always_smem=True))
+    return out
+
+
 def bluestein_entries(f64):
     """Fused Bluestein kernels: M-point family-B schedules (rows: one tile shape, columns: the two widest that fit)."""
     out = []
@@ -358,7 +374,7 @@ def main():
     total += len(ents)
     rnames = []
     for f64 in (0, 1):
-        ents = real_entries(f64)
+        ents = real_entries(f64) + alt_real_entries(f64)
         for kind in ["RK_R2C", "RK_C2R", "RK_DCT1", "RK_DCT2", "RK_DCT3", "RK_DCT4"]:
             nm = f"{'f64' if f64 else 'f32'}_{kind[3:].lower()}"
             write(f"rsfft_inst_{nm}.cu", head + [f"const RsfftEntry kRsfft_{nm}[] = {{"] + [fmt(e, "RSFFT_ENTRY", kind + ", ") for e in ents] +
