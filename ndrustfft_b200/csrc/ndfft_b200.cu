@@ -835,6 +835,17 @@ static const RsfftEntry* find_rsfft(bool f64, int rkind, int N, bool cols, long 
     // Measured on B200 (profiles/round2/r2m_ab_mirror_first_pass.txt): the saved prologue round trip does not pay for the
     // radix-4-first schedule (c3 ndifft_r2c 0.426 -> 0.460 ms, DCT-III rows 0.109 = 0.109 ms, columns 0.146 -> 0.141 ms),
     // so it is opt-in: NDFB_MIRROR_PRO=1.
+    // Measured choices the generic rules below cannot see (same-box A/B, profiles/round2/r3i_ab_dct1_schedules.jsonl): the 4095-point core
+    // as 15.13.7.3 on 320 threads keeps 88 % of its thread slots busy against 71 % for 13.9.7.5 on 512 (DCT-I of 4096 points, c4):
+    // f64 rows 0.164 -> 0.146 ms with two CTAs per SM (three spill: 0.218 ms), f32 rows 0.173 -> 0.150 ms with three, f64 columns +4 %.
+    if (N == 4095 && !std::getenv("NDFB_NO_TUNED_PICKS")) {
+        const int want_minb = cols ? 1 : (f64 ? 2 : 3);
+        for (const Tab& t : tabs)
+            for (int i = 0; i < t.n; ++i) {
+                const RsfftEntry* e = &t.e[i];
+                if (e->f64 == (f64 ? 1 : 0) && e->kind == rkind && e->N == N && e->cols == (cols ? 1 : 0) && e->r[0] == 15 && e->minb == want_minb) return e;
+            }
+    }
     const bool wants_rev = (rkind == RK_C2R || rkind == RK_DCT3) && std::getenv("NDFB_MIRROR_PRO") != nullptr;
     const int pref = wants_rev ? 2 : preferred_family(f64, N, cols, true);
     const RsfftEntry* best = nullptr;

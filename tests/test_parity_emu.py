@@ -577,11 +577,11 @@ def test_schedule_selection_for_the_baseline_shapes(hs, capfd):
         assert "N=512 cols L=8 T=512" in e and "fam=B" in e, e
         e = trace("ndfft_r2c", be.R2cFftHandler(512), (4, 4, 512), (4, 4, 257), 2, cplx_in=False)
         assert "rsfft kind=0 f64 N=256 rows L=8 T=256" in e, e
-        # c4: DCT-I of 4096 points = 4095-point core, capped row variant and the two-column strided tile
+        # c4: DCT-I of 4096 points = 4095-point core as 15.13.7.3 on 320 threads (two CTAs per SM in f64) and the two-column strided tile
         e = trace("nddct1", be.DctHandler(4096), (2, 4096), (2, 4096), 1, cplx_in=False, cplx_out=False)
-        assert "N=4095 rows L=1 T=512" in e and "minb=2" in e, e
+        assert "N=4095 rows L=1 T=320" in e and "minb=2" in e, e
         e = trace("nddct1", be.DctHandler(4096), (4096, 4), (4096, 4), 0, cplx_in=False, cplx_out=False)
-        assert "N=4095 cols L=2 T=1024" in e, e
+        assert "N=4095 cols L=2 T=640" in e, e
         # c2: 8192-point c64 rows = family B 16.16.16.2 with 512 threads; strided columns = two passes 64 x 128
         e = trace("ndfft", be.FftHandler(8192, np.float32), (2, 8192), (2, 8192), 1, rd=np.float32)
         assert "N=8192 rows L=1 T=512" in e and "fam=B" in e and "minb=2" in e, e
