@@ -768,3 +768,18 @@ def test_default_split_rules_at_real_sizes(hs, capfd):
         assert "four-step N=2097152 = 256 x 8192 (contiguous lanes, second factor split again)" in err, err
     finally:
         del os.environ["NDFB_TRACE"]
+
+
+@pytest.mark.parametrize("op", ["ndfft_r2c", "ndifft_r2c", "nddct2", "nddct3", "nddct4"])
+def test_real_kinds_on_the_4095_point_core(hs, op, capfd):
+    """n = 8190 = 2 x 4095: every even-length real kind runs the 4095-point core, i.e. the measured schedule pick 15.13.7.3 on 320
+    threads (unpadded: odd first radix), rows and columns, both precisions."""
+    import os
+    os.environ["NDFB_TRACE"] = "1"
+    try:
+        hs.run(op, 8190, (2, 8190), 1, np.float64, seed=3)
+        hs.run(op, 8190, (8190, 3), 0, np.float32, seed=4)
+    finally:
+        del os.environ["NDFB_TRACE"]
+    err = capfd.readouterr().err
+    assert "N=4095 rows L=1 T=320" in err and "N=4095 cols L=2 T=640" in err, err
