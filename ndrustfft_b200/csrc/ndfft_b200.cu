@@ -556,8 +556,10 @@ static int launch_sfft(ndfb_plan* p, const SfftEntry* e, const LaunchSpec& s, st
     a.trans_store = trans_next ? 1 : 0;
     // Column tiles whose lanes are consecutive j2 (the lane dim IS the twiddle dim and holds whole tiles): the four-step twiddle is
     // formed as (tile-uniform hi/lo lookup) x (coalesced [k][l] table) instead of one scattered lookup per point (MODE 4).
+    // (whole tiles only: every thread of the CTA derives the same tile base j20 from its own lane, and the tile's factor needs N more
+    // elements of shared memory behind the exchange buffer, which must still fit the SM)
     if (s.fs_twiddle && e->cols && s.fs_dim == 0 && !s.os_blk && !s.nblk_ptr && !s.dims.empty() && s.dims[0].size % e->L == 0 && s.fs.ntot &&
-        !std::getenv("NDFB_NO_FS_FACTORED")) {
+        e->smem + (size_t)e->N * sizeof(Cx<R>) <= dev_smem_cap(p->device) && !std::getenv("NDFB_NO_FS_FACTORED")) {
         void* tq = nullptr;
         int rc = get_fs_kl<R>(p, s.fs.ntot, e->N, e->L, &tq);
         if (rc) return rc;
