@@ -7,7 +7,6 @@ CODE = r'''
 import sys, json, os
 sys.path.insert(0, %r)
 import numpy as np, torch, ndrustfft_b200 as nb
-from oracle import ndrustfft_oracle as orc
 shape = tuple(int(v) for v in os.environ["SHAPE"].split("x")); axis = int(os.environ["AXIS"]); f64 = os.environ["F64"] == "1"; op = os.environ["OP"]
 rt = torch.float64 if f64 else torch.float32
 rd = np.float64 if f64 else np.float32
@@ -27,17 +26,26 @@ for _ in range(10):
     for _ in range(reps): f(x, y, h, axis)
     e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / reps)
 ts.sort()
-idx = [slice(None)] * len(shape)
-for d in range(len(shape)):
-    if d != axis: idx[d] = slice(0, 3)
-xs = x[tuple(idx)].cpu().numpy(); ys = y[tuple(idx)].cpu().numpy()
-ho = (orc.FftHandler if cx else orc.DctHandler)(n)
-want = np.zeros(xs.shape, np.complex128 if cx else np.float64)
-getattr(orc, op)(xs.astype(np.complex128 if cx else np.float64), want, ho, axis)
+# (timing tool only: parity against the oracle is the job of tests/; here a direct O(n^2) f64 sum of ONE output element per kind
+# guards against measuring a broken path)
+def direct(op, v, k):
+    m = np.arange(n)
+    if op == "nddct1":
+        return 2 * (0.5 * (v[0] + (-1) ** k * v[-1]) + np.sum(v[1:-1] * np.cos(np.pi * m[1:-1] * k / (n - 1))))
+    if op == "nddct2": return 2 * np.sum(v * np.cos(np.pi * (m + 0.5) * k / n))
+    if op == "nddct3": return 2 * (0.5 * v[0] + np.sum(v[1:] * np.cos(np.pi * m[1:] * (k + 0.5) / n)))
+    if op == "nddct4": return 2 * np.sum(v * np.cos(np.pi * (m + 0.5) * (k + 0.5) / n))
+    return np.sum(v * np.exp(-2j * np.pi * m * k / n))
+idx = [0] * len(shape); idx[axis] = slice(None)
+lane_in = x[tuple(idx)].cpu().numpy().astype(np.complex128 if cx else np.float64)
+lane_out = y[tuple(idx)].cpu().numpy()
+k = n // 3
+want = direct(op, lane_in, k)
+rel = float(abs(lane_out[k] - want) / (abs(want) + 1e-300))
 ms = ts[len(ts) // 2]
 nbytes = 2 * x.numel() * x.element_size()
 print(json.dumps({"case": os.environ["CASE"], "variant": os.environ["VARIANT"], "ms": round(ms, 4), "ms_min": round(ts[0], 4),
-                  "frac": round(nbytes / (ms * 1e-3) / 1e9 / 6547.8, 4), "rel_l2": orc.rel_l2(ys, want)}))
+                  "frac": round(nbytes / (ms * 1e-3) / 1e9 / 6547.8, 4), "rel_err_one_element": rel}))
 ''' % ROOT
 V2 = [("staged copy-out", {"NDFB_NO_MIRROR_OUT": "1"}), ("mirror-paired output pass", {})]
 D1R = [("13.9.7.5 on 512 threads, 2 CTAs/SM", {"NDFB_RSFFT_PICK": "4095:1"}), ("15.13.7.3 on 320 threads, 2 CTAs/SM", {"NDFB_RSFFT_PICK": "4095:2"}),
